@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- ALS ratings/s per sweep (headline) on synthetic data of the BASELINE.json shapes.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1] [--impl ours|reference]
+
+One step = one ALS sweep (item half-step, all-gather, user half-step, all-gather) over the
+whole ratings matrix, factors and CSR shards resident in HBM.  `value` = nnz / (time per sweep),
+whole job, max over ranks.  `e2e` = the same metric through the public `train()`-shaped path
+with HOST inputs: pinned COO triples -> H2D -> CSR build + plan -> `e2e_sweeps` sweeps -> factors
+D2H, all inside the timed region.  `roofline` is the half-step kernel sequence against the
+measured HBM peak with SURVEY.md 8(d) algorithmic bytes; `cpu_baseline` is the CPU oracle port
+(Spark local[N] cannot run in this image) on a bounded row sample.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (users, items, nnz, rank, reg, rating grid)
+    "c1": dict(users=10_000, items=10_000, nnz=10_000, rank=10, reg=0.1, half=False,
+               desc="synthetic Amazon-sample shape 10k x 10k, ~10k ratings, rank 10"),
+    "c2": dict(users=138_493, items=26_744, nnz=20_000_263, rank=64, reg=0.1, half=True,
+               desc="MovieLens-20M shape 138,493 x 26,744, 20,000,263 ratings, explicit ALS rank 64"),
+    "c3": dict(users=480_189, items=17_770, nnz=100_480_507, rank=128, reg=0.1, half=False,
+               desc="Netflix-prize shape 480,189 x 17,770, 100,480,507 ratings, explicit ALS rank 128"),
+}
+METRIC = "als_ratings_per_sec_per_sweep"
+UNIT = "ratings/s"
+
+
+def synth_coo(w, device, seed=1234):
+    """Zipf item popularity (exponent 1), log-normal user activity, duplicates kept (Spark does not
+    merge them).  Generated on `device` with a fixed seed: identical on every rank."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    U, I, nnz = w["users"], w["items"], w["nnz"]
+    item_p = 1.0 / torch.arange(1, I + 1, device=device, dtype=torch.float64)
+    perm = torch.randperm(I, generator=g, device=device)
+    item_w = torch.empty_like(item_p)
+    item_w[perm] = item_p                                  # popularity not sorted by id
+    user_w = torch.exp(torch.randn(U, generator=g, device=device, dtype=torch.float64) * 1.0)
+    chunks_u, chunks_i = [], []
+    left = nnz
+    while left > 0:
+        n = min(left, 1 << 24)
+        chunks_u.append(torch.multinomial(user_w.float(), n, replacement=True, generator=g))
+        chunks_i.append(torch.multinomial(item_w.float(), n, replacement=True, generator=g))
+        left -= n
+    u = torch.cat(chunks_u).to(torch.int32)
+    i = torch.cat(chunks_i).to(torch.int32)
+    if w["half"]:
+        r = torch.randint(1, 11, (nnz,), generator=g, device=device).float() * 0.5
+    else:
+        r = torch.randint(1, 6, (nnz,), generator=g, device=device).float()
+    return u, i, r
+
+
+def algorithmic_bytes(w):
+    k, nnz = w["rank"], w["nnz"]
+    item_half = nnz * (8 + 4 * k) + w["items"] * (4 * k + 4)
+    user_half = nnz * (8 + 4 * k) + w["users"] * (4 * k + 4)
+    return item_half, user_half
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on a bounded row sample
+# ------------------------------------------------------------------------------------------
+def cpu_baseline_run(w, u, i, r, target_nnz=1_500_000, seed=3):
+    from oracle import als_oracle, c_oracle
+    U, I, k = w["users"], w["items"], w["rank"]
+    t0 = time.time()
+    X = als_oracle.init_factors(U, k, seed)
+    ir, ic, iv = als_oracle.coo_to_csr(i, u, r, I)
+    ur, uc, uv = als_oracle.coo_to_csr(u, i, r, U)
+
+    def sample_rows(rowptr, n):
+        mid = n // 3
+        end = int(np.searchsorted(rowptr, rowptr[mid] + min(target_nnz, rowptr[-1] - rowptr[mid])))
+        end = max(min(end, n), mid + 1)
+        return mid, end, int(rowptr[end] - rowptr[mid])
+
+    ib, ie, inz = sample_rows(ir, I)
+    ub, ue, unz = sample_rows(ur, U)
+    prep = time.time() - t0
+    Y = np.zeros((I, k), np.float32)
+    t0 = time.time()
+    c_oracle.als_half_step(ir, ic, iv, X, w["reg"], row_begin=ib, row_end=ie, out=Y)
+    ti = time.time() - t0
+    Yfull = als_oracle.init_factors(I, k, seed + 1)
+    t0 = time.time()
+    c_oracle.als_half_step(ur, uc, uv, Yfull, w["reg"], row_begin=ub, row_end=ue)
+    tu = time.time() - t0
+    per_rating = ti / max(inz, 1) + tu / max(unz, 1)          # seconds per rating per sweep
+    return {"value": 1.0 / per_rating, "unit": UNIT, "cores": c_oracle.num_threads(), "kind": "port",
+            "sample": f"item rows [{ib},{ie}) = {inz} ratings in {ti:.2f}s + user rows [{ub},{ue}) = {unz} ratings "
+                      f"in {tu:.2f}s of the {w['nnz']}-rating workload (C oracle, fp64 packed dspr + dppsv, OpenMP); "
+                      f"Spark local[N] unavailable offline", "prep_s": round(prep, 2)}
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's CPU path restated (oracle port; pyspark/JVM absent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    u, i, r = synth_coo(w, "cpu")
+    u, i, r = u.numpy(), i.numpy(), r.numpy()
+    vals = []
+    res = None
+    for s in range(args.warmup + args.steps):
+        res = cpu_baseline_run(w, u, i, r, target_nnz=args.cpu_sample)
+        if s >= args.warmup:
+            vals.append(res["value"])
+    v = float(np.mean(vals))
+    res["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * w["nnz"] / v, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "note": "CPU oracle port of Spark ALS on host cores; "
+                       "ms_per_step extrapolated from the bounded sample to a full sweep"},
+            "cpu_baseline": res, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-sweeps", type=int, default=10, help="sweeps per end-to-end train()-shaped call")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=1_500_000, help="ratings per half-step in the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    import torch
+    import torch.distributed as dist
+    import hybrid_als_twotower_recommender_b200  # noqa: F401
+    from hybrid_als_twotower_recommender_b200 import _native as nat
+    from hybrid_als_twotower_recommender_b200.als_engine import AlsEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    nat.lib()
+    nat.require_cuda()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+
+    u, i, r = synth_coo(w, dev)
+    eng = AlsEngine(u, i, r, w["users"], w["items"], w["rank"], w["reg"], device=dev, dist_rank=rank, world=world)
+    eng.init_user_factors(1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        eng.sweep()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    l0 = nat.launch_count()
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.steps):
+        ev[s][0].record(); eng.item_half_step(); ev[s][1].record()
+        ev[s][2].record(); eng.user_half_step(); ev[s][3].record()
+    t_end.record()
+    barrier()
+    launches = nat.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_start.elapsed_time(t_end)
+    t_item = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    t_user = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
+    tm = torch.tensor([total_ms, t_item, t_user], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms, t_item, t_user = (float(x) for x in tm.tolist())
+    ms_per_step = total_ms / args.steps
+    value = w["nnz"] / (ms_per_step * 1e-3)
+    rmse_train = eng.rmse(u[:1_000_000], i[:1_000_000], r[:1_000_000])
+
+    # ---- end-to-end: host COO in pinned memory -> H2D -> CSR + plan -> sweeps -> factors D2H ----------
+    hu, hi, hr = (t.cpu().pin_memory() for t in (u, i, r))
+    X0 = eng.X.clone()
+    del eng
+    torch.cuda.empty_cache()
+    e2e_ms = []
+    hX = torch.empty((w["users"], w["rank"]), dtype=torch.float32).pin_memory()
+    hY = torch.empty((w["items"], w["rank"]), dtype=torch.float32).pin_memory()
+    for s in range(1 + args.e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        du, di, dr = hu.to(dev, non_blocking=True), hi.to(dev, non_blocking=True), hr.to(dev, non_blocking=True)
+        e = AlsEngine(du, di, dr, w["users"], w["items"], w["rank"], w["reg"], device=dev, dist_rank=rank, world=world)
+        e.X.copy_(X0)
+        e.fit(args.e2e_sweeps)
+        hX.copy_(e.X, non_blocking=True); hY.copy_(e.Y, non_blocking=True)
+        barrier()
+        if s > 0:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        del e
+    te = torch.tensor([float(np.mean(e2e_ms))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = args.e2e_sweeps * w["nnz"] / (float(te) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    b_item, b_user = algorithmic_bytes(w)
+    # per-rank share of the algorithmic bytes (rows are nnz-balanced across ranks)
+    ach = (b_item + b_user) / world / ((t_item + t_user) * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "step": "one ALS sweep = item half-step + user half-step "
+                   "(+ factor all-gathers when sharded)", "rows": "nnz-balanced contiguous row shards per rank",
+                   "l2": "per-step inputs (2 CSR orientations + factors) exceed the 126 MB L2; no flush between steps",
+                   "train_rmse_after_run": rmse_train},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(w["nnz"] * 12),
+                "d2h_bytes_per_step": int((w["users"] + w["items"]) * w["rank"] * 4), "sweeps_per_call": args.e2e_sweeps,
+                "ms_per_call": float(te), "what": "pinned host COO -> H2D -> CSR build + plan -> sweeps -> factors D2H"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "kernel": "als half-step (build normal equations + Cholesky solve), item + user launches",
+                     "algorithmic_bytes_per_sweep": b_item + b_user, "ms_item_half": t_item, "ms_user_half": t_user,
+                     "peak_source": peak_src},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_run(w, hu.numpy(), hi.numpy(), hr.numpy(), target_nnz=args.cpu_sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

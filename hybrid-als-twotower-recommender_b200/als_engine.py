@@ -1,0 +1,163 @@
+"""ALS sweeps on B200: the replacement for `ALS(...).fit(df)` (src/als_model.py:52-62).
+
+One process per GPU.  Rank r owns an nnz-balanced contiguous range of user rows of R and
+of item rows of R^T (CSR shards resident in HBM) plus full replicas of both factor
+matrices.  A sweep is   item half-step -> all-gather(Y) -> user half-step -> all-gather(X)
+(Spark's loop order; ALS.scala train).  The half-step itself is one C-ABI call
+(hals_als_half_step); the all-gather is NCCL through torch.distributed.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .csr import AlsPlanHandle, CsrShard, balanced_row_bounds, build_csr
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+def all_gather_rows(full: torch.Tensor, bounds, rank: int, world: int, group=None):
+    """All-gather of uneven contiguous row shards of `full` ([n,k], every rank holds the whole
+    buffer, its own rows freshly written).  Shards are padded to the largest one so a single
+    equal-size all-gather moves them (NCCL ring/NVLS over NVLink), then unpacked in place."""
+    dist = _dist()
+    if dist is None or world == 1:
+        return
+    k = full.shape[1]
+    sizes = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
+    mx = max(sizes)
+    if mx == 0:
+        return
+    send = torch.zeros((mx, k), dtype=full.dtype, device=full.device)
+    send[: sizes[rank]] = full[int(bounds[rank]): int(bounds[rank + 1])]
+    recv = torch.empty((world, mx, k), dtype=full.dtype, device=full.device)
+    if full.is_cuda:
+        dist.all_gather_into_tensor(recv.view(world * mx, k), send, group=group)
+    else:  # gloo (CPU tests)
+        parts = list(recv.unbind(0))
+        dist.all_gather(parts, send, group=group)
+    for r in range(world):
+        if r != rank and sizes[r]:
+            full[int(bounds[r]): int(bounds[r + 1])] = recv[r, : sizes[r]]
+
+
+def native_half_step(shard: CsrShard, plan: AlsPlanHandle, src: torch.Tensor, dst_full: torch.Tensor,
+                     k: int, reg: float, implicit: bool, alpha: float, gram: torch.Tensor | None):
+    """dst_full[row_begin:row_end] = solve(shard, src).  The only compute path (CUDA)."""
+    L = nat.lib()
+    dst = dst_full[shard.row_begin: shard.row_end]
+    assert src.is_contiguous() and dst.is_contiguous() and src.dtype == torch.float32
+    nat.check(L.hals_als_half_step(
+        nat.ptr(shard.rowptr), nat.ptr(shard.colidx), nat.ptr(shard.vals), shard.n_rows,
+        nat.ptr(src), src.shape[0], nat.ptr(dst), k, float(reg), int(bool(implicit)), float(alpha),
+        nat.ptr(gram) if gram is not None else None, plan.struct, nat.ptr(plan.workspace),
+        plan.workspace_bytes, nat.current_stream()), "hals_als_half_step")
+
+
+def native_gram(src: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor):
+    L = nat.lib()
+    nat.check(L.hals_gram(nat.ptr(src), src.shape[0], src.shape[1], nat.ptr(out), nat.ptr(workspace),
+                          workspace.numel(), nat.current_stream()), "hals_gram")
+
+
+class AlsEngine:
+    """Device-resident state of one ALS fit on this rank."""
+
+    def __init__(self, users, items, ratings, n_users: int, n_items: int, rank: int, reg: float,
+                 implicit: bool = False, alpha: float = 1.0, device=None, seg_len: int | None = None,
+                 dist_rank: int = 0, world: int = 1, half_step=None, make_plans: bool = True):
+        self.k, self.reg, self.implicit, self.alpha = int(rank), float(reg), bool(implicit), float(alpha)
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        self.rank, self.world = dist_rank, world
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self._half_step = half_step or native_half_step
+        users = torch.as_tensor(users).to(self.device)
+        items = torch.as_tensor(items).to(self.device)
+        ratings = torch.as_tensor(ratings).to(self.device, torch.float32)
+        self.nnz_total = int(users.numel())
+        # nnz-balanced contiguous row ranges (identical on every rank: computed from global counts)
+        ucnt = torch.bincount(users.to(torch.int64), minlength=n_users).cpu().numpy()
+        icnt = torch.bincount(items.to(torch.int64), minlength=n_items).cpu().numpy()
+        self.user_bounds = balanced_row_bounds(ucnt, world)
+        self.item_bounds = balanced_row_bounds(icnt, world)
+        self.user_present = torch.from_numpy(ucnt > 0).to(self.device)
+        self.item_present = torch.from_numpy(icnt > 0).to(self.device)
+        ub, ue = int(self.user_bounds[dist_rank]), int(self.user_bounds[dist_rank + 1])
+        ib, ie = int(self.item_bounds[dist_rank]), int(self.item_bounds[dist_rank + 1])
+        self.R = build_csr(users, items, ratings, n_users, ub, ue)       # user rows -> item columns
+        self.Rt = build_csr(items, users, ratings, n_items, ib, ie)      # item rows -> user columns
+        self.plan_R = self.plan_Rt = None
+        if make_plans:
+            self.plan_R = AlsPlanHandle(self.R, self.k, seg_len)
+            self.plan_Rt = AlsPlanHandle(self.Rt, self.k, seg_len)
+        self.X = torch.zeros((n_users, self.k), dtype=torch.float32, device=self.device)
+        self.Y = torch.zeros((n_items, self.k), dtype=torch.float32, device=self.device)
+        self.gram = None
+        self.gram_ws = None
+        if self.implicit:
+            self.gram = torch.zeros((self.k, self.k), dtype=torch.float32, device=self.device)
+            if self.device.type == "cuda":
+                self.gram_ws = torch.empty(int(nat.lib().hals_gram_workspace_bytes(self.k)), dtype=torch.uint8,
+                                           device=self.device)
+
+    # -- factors ---------------------------------------------------------------------------
+    def set_user_factors(self, X0):
+        self.X.copy_(torch.as_tensor(X0, dtype=torch.float32).to(self.device))
+
+    def init_user_factors(self, seed: int = 0):
+        """Spark's `initialize` distribution: N(0,1) rows scaled to unit L2 norm."""
+        g = torch.Generator(device="cpu").manual_seed(int(seed))
+        f = torch.randn((self.n_users, self.k), generator=g, dtype=torch.float32)
+        f = f / f.norm(dim=1, keepdim=True).clamp_min(1e-30)
+        self.X.copy_(f.to(self.device))
+
+    def _gram_of(self, src):
+        if not self.implicit:
+            return None
+        if self._half_step is native_half_step:
+            native_gram(src, self.gram, self.gram_ws)
+        else:  # injected half-step (CPU tests): it computes its own Gram
+            return None
+        return self.gram
+
+    # -- one sweep = item half-step, then user half-step (Spark's order) ---------------------
+    def item_half_step(self):
+        self._half_step(self.Rt, self.plan_Rt, self.X, self.Y, self.k, self.reg, self.implicit, self.alpha,
+                        self._gram_of(self.X))
+        all_gather_rows(self.Y, self.item_bounds, self.rank, self.world)
+
+    def user_half_step(self):
+        self._half_step(self.R, self.plan_R, self.Y, self.X, self.k, self.reg, self.implicit, self.alpha,
+                        self._gram_of(self.Y))
+        all_gather_rows(self.X, self.user_bounds, self.rank, self.world)
+
+    def sweep(self):
+        self.item_half_step()
+        self.user_half_step()
+
+    def fit(self, max_iter: int):
+        for _ in range(int(max_iter)):
+            self.sweep()
+        return self.X, self.Y
+
+    # -- evaluation helpers -------------------------------------------------------------------
+    def rmse(self, users, items, ratings) -> float:
+        L = nat.lib()
+        users = torch.as_tensor(users).to(self.device, torch.int32).contiguous()
+        items = torch.as_tensor(items).to(self.device, torch.int32).contiguous()
+        ratings = torch.as_tensor(ratings).to(self.device, torch.float32).contiguous()
+        sse = torch.zeros(1, dtype=torch.float64, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        nat.check(L.hals_als_sse(nat.ptr(self.X), nat.ptr(self.Y), self.k, nat.ptr(users), nat.ptr(items),
+                                 nat.ptr(ratings), users.numel(), nat.ptr(sse), nat.ptr(cnt),
+                                 nat.current_stream()), "hals_als_sse")
+        return float(torch.sqrt(sse / cnt.clamp_min(1)).item())
+
+    def algorithmic_bytes_per_sweep(self) -> int:
+        """per half-step nnz*(8+4k) + m_dst*(4k+4); item + user half-steps."""
+        k = self.k
+        return int(2 * self.nnz_total * (8 + 4 * k) + (self.n_users + self.n_items) * (4 * k + 4))

@@ -1,0 +1,271 @@
+"""ALSModel -- drop-in for the reference's src/als_model.py (class at :21-140).
+
+Same constructor, attributes, method names, return conventions (print + sentinel on error,
+als_model.py:64-66,89-91,120-121,134-136).  What changed is what sits behind `train` and
+`predict_for_user`: instead of pyspark.ml ALS.fit / ALSModel.transform over Py4J
+(als_model.py:52-62,75) the factors are solved and scored by the sm_100a kernels of
+libhals_b200.so (csrc/), driven by als_engine.AlsEngine.
+
+Additive (keyword-only) extensions, none of which changes the reference behaviour:
+  ALSModel(..., implicit_prefs=False, alpha=1.0, seed=0)   Spark's implicitPrefs / alpha / seed
+  train(data, init_user_factors=None)                      explicit initial factors for parity runs
+  predict_for_users(user_ids, item_ids)                    dense [U,I] block of scores (device)
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from .data_preprocessing import get_item_features
+
+warnings.filterwarnings("ignore")
+
+
+class _Backend:
+    """Stands where the reference keeps its SparkSession (`self.spark`, als_model.py:28,34-37)."""
+
+    def __init__(self):
+        from . import _native as nat
+        nat.lib()
+        nat.require_cuda()
+        self.active = True
+
+    def stop(self):
+        self.active = False
+
+
+class ALSFactors:
+    """The fitted model (what pyspark's ALSModel holds): factor tables keyed by raw id."""
+
+    def __init__(self, rank, user_ids, item_ids, user_factors, item_factors, user_present, item_present):
+        self.rank = rank
+        self.user_ids = np.asarray(user_ids)          # sorted raw ids; row i of the table <-> user_ids[i]
+        self.item_ids = np.asarray(item_ids)
+        self.user_factors = user_factors              # torch fp32 [U,k] on the device
+        self.item_factors = item_factors              # torch fp32 [I,k]
+        self.user_present = user_present
+        self.item_present = item_present
+
+    def user_row(self, user_id):
+        i = int(np.searchsorted(self.user_ids, user_id))
+        return i if i < len(self.user_ids) and self.user_ids[i] == user_id else -1
+
+    def item_rows(self, items):
+        items = np.asarray(items)
+        pos = np.searchsorted(self.item_ids, items)
+        pos = np.clip(pos, 0, max(len(self.item_ids) - 1, 0))
+        ok = (self.item_ids[pos] == items) if len(self.item_ids) else np.zeros(len(items), bool)
+        return np.where(ok, pos, -1)
+
+
+def _as_item_ids(all_items):
+    """The reference hands the same `all_items` to both predictors (hybrid_system.py:101-102)
+    although ALS wants ids and the two-tower model wants a DataFrame: accept both."""
+    if isinstance(all_items, pd.DataFrame):
+        return list(all_items["itemId"].values)
+    return list(all_items)
+
+
+class ALSModel:
+    def __init__(self, rank=10, max_iter=10, reg_param=0.1, cold_start_strategy="drop", *,
+                 implicit_prefs=False, alpha=1.0, seed=0):
+        self.rank = rank
+        self.max_iter = max_iter
+        self.reg_param = reg_param
+        self.cold_start_strategy = cold_start_strategy
+        self.model = None
+        self.spark = None
+        self.global_mean = 3.0
+        self.item_features = None
+        self.implicit_prefs = implicit_prefs
+        self.alpha = alpha
+        self.seed = seed
+
+    def initialize_spark(self):
+        try:
+            if self.spark is None or not getattr(self.spark, "active", False):
+                self.spark = _Backend()
+            return True
+        except Exception as e:
+            print(f"Spark init error: {str(e)}")
+            return False
+
+    def train(self, data, init_user_factors=None):
+        try:
+            if not self.initialize_spark():
+                return False
+            import torch
+            from .als_engine import AlsEngine
+
+            self.item_features = get_item_features(data)
+            self.global_mean = data["average_review_rating"].mean()
+
+            user_ids, u = np.unique(data["userId"].values, return_inverse=True)
+            item_ids, i = np.unique(data["itemId"].values, return_inverse=True)
+            r = data["average_review_rating"].values.astype(np.float32)
+            eng = AlsEngine(torch.from_numpy(u.astype(np.int64)), torch.from_numpy(i.astype(np.int64)),
+                            torch.from_numpy(r), len(user_ids), len(item_ids), self.rank, self.reg_param,
+                            implicit=self.implicit_prefs, alpha=self.alpha)
+            if init_user_factors is not None:
+                eng.set_user_factors(init_user_factors)
+            else:
+                eng.init_user_factors(self.seed)
+            eng.fit(self.max_iter)
+            torch.cuda.synchronize()
+            self.model = ALSFactors(self.rank, user_ids, item_ids, eng.X, eng.Y, eng.user_present, eng.item_present)
+            return True
+        except Exception as e:
+            print(f"Training error: {str(e)}")
+            return False
+
+    def predict_for_user(self, user_id, all_items):
+        try:
+            import torch
+            from . import _native as nat
+            items = _as_item_ids(all_items)
+            m = self.model
+            urow = m.user_row(user_id)
+            rows = m.item_rows(items) if len(items) else np.zeros(0, np.int64)
+            known = rows >= 0
+            scores = np.full(len(items), np.nan, dtype=np.float32)
+            if urow >= 0 and known.any():
+                dev = m.item_factors.device
+                ids = torch.from_numpy(rows[known].astype(np.int32)).to(dev)
+                out = torch.empty(ids.numel(), dtype=torch.float32, device=dev)
+                nat.check(nat.lib().hals_score_one_user(
+                    nat.ptr(m.user_factors[urow]), nat.ptr(m.item_factors), m.item_factors.stride(0), m.rank,
+                    nat.ptr(ids), ids.numel(), nat.ptr(out), nat.current_stream()), "hals_score_one_user")
+                scores[known] = out.cpu().numpy()
+            final_preds = []
+            for item, s in zip(items, scores):
+                if not np.isnan(s):
+                    final_preds.append((item, float(s)))
+                else:  # cold user / cold item: content-similar fallback, as als_model.py:82-86
+                    similar_items = self._find_similar_items(item)
+                    placeholder = np.mean([self.item_features[sim_item]["rating"]
+                                           for sim_item in similar_items]) if similar_items else self.global_mean
+                    final_preds.append((item, placeholder))
+            return final_preds
+        except Exception as e:
+            print(f"Prediction error: {str(e)}")
+            return []
+
+    def predict_for_users(self, user_ids, item_ids):
+        """Additive batched entry point: [len(user_ids), len(item_ids)] fp32 scores on the device
+        (NaN where the user or item is unknown, Spark's coldStartStrategy='nan' view)."""
+        import torch
+        from . import _native as nat
+        m = self.model
+        urows = np.array([m.user_row(u) for u in user_ids], dtype=np.int64)
+        irows = m.item_rows(item_ids)
+        dev = m.item_factors.device
+        uu = torch.from_numpy(np.repeat(np.maximum(urows, 0), len(irows)).astype(np.int32)).to(dev)
+        ii = torch.from_numpy(np.tile(np.maximum(irows, 0), len(urows)).astype(np.int32)).to(dev)
+        out = torch.empty(uu.numel(), dtype=torch.float32, device=dev)
+        nat.check(nat.lib().hals_als_predict(nat.ptr(m.user_factors), nat.ptr(m.item_factors), m.rank, nat.ptr(uu),
+                                             nat.ptr(ii), uu.numel(), None, None, nat.ptr(out),
+                                             nat.current_stream()), "hals_als_predict")
+        out = out.view(len(urows), len(irows))
+        bad = torch.from_numpy((urows < 0)[:, None] | (irows < 0)[None, :]).to(dev)
+        return out.masked_fill(bad, float("nan"))
+
+    def _find_similar_items(self, item_id, k=3):
+        """Top-k cosine-similar items with similarity > 0.5 (als_model.py:93-104), vectorised."""
+        try:
+            target = self.item_features[item_id]
+            ids = [i for i in self.item_features if i != item_id]
+            if not ids:
+                return []
+            F = np.asarray([self.item_features[i]["features"] for i in ids], dtype=np.float64)
+            t = np.asarray(target["features"], dtype=np.float64)
+            denom = np.linalg.norm(F, axis=1) * np.linalg.norm(t)
+            sim = np.divide(F @ t, denom, out=np.zeros(len(ids)), where=denom > 0)
+            order = np.argsort(-sim, kind="stable")[:k]
+            return [ids[j] for j in order if sim[j] > 0.5]
+        except (KeyError, TypeError):
+            return []
+
+    def save_model(self, model_path="models/als"):
+        try:
+            os.makedirs(os.path.dirname(model_path) or ".", exist_ok=True)
+            m = self.model
+            np.savez(f"{model_path}.npz", rank=m.rank, user_ids=m.user_ids, item_ids=m.item_ids,
+                     user_factors=m.user_factors.cpu().numpy(), item_factors=m.item_factors.cpu().numpy(),
+                     user_present=m.user_present.cpu().numpy(), item_present=m.item_present.cpu().numpy())
+            metadata = {
+                "rank": self.rank,
+                "max_iter": self.max_iter,
+                "reg_param": self.reg_param,
+                "global_mean": self.global_mean,
+                "item_features": self.item_features,
+            }
+            with open(f"{model_path}_metadata.pkl", "wb") as f:
+                pickle.dump(metadata, f)
+            print(f"Model saved to {model_path}")
+        except Exception as e:
+            print(f"Saving error: {str(e)}")
+
+    def load_model(self, model_path="models/als"):
+        try:
+            import torch
+            if not self.initialize_spark():
+                return None
+            z = np.load(f"{model_path}.npz")
+            dev = torch.device("cuda")
+            self.model = ALSFactors(int(z["rank"]), z["user_ids"], z["item_ids"],
+                                    torch.from_numpy(z["user_factors"]).to(dev),
+                                    torch.from_numpy(z["item_factors"]).to(dev),
+                                    torch.from_numpy(z["user_present"]).to(dev),
+                                    torch.from_numpy(z["item_present"]).to(dev))
+            with open(f"{model_path}_metadata.pkl", "rb") as f:
+                metadata = pickle.load(f)
+                self.rank = metadata["rank"]
+                self.max_iter = metadata["max_iter"]
+                self.reg_param = metadata["reg_param"]
+                self.global_mean = metadata["global_mean"]
+                self.item_features = metadata["item_features"]
+            return self
+        except Exception as e:
+            print(f"Loading error: {str(e)}")
+            return None
+
+    def stop_spark(self):
+        if self.spark:
+            self.spark.stop()
+
+
+def hyperparameter_tuning(train_data, val_data, param_grid):
+    """F1 grid search, as als_model.py:142-169."""
+    best_params = None
+    best_f1 = 0.0
+    for params in param_grid:
+        model = ALSModel(**params)
+        if not model.train(train_data):
+            continue
+        f1_scores = []
+        for user_id in val_data["userId"].sample(min(50, len(val_data))).unique():
+            sel = val_data[val_data["userId"] == user_id]
+            actual = dict(zip(sel["itemId"], sel["average_review_rating"]))
+            preds = model.predict_for_user(user_id, val_data["itemId"].unique())
+            f1_scores.append(compute_f1_score(actual, {item: score for item, score in preds}))
+        avg_f1 = np.mean(f1_scores)
+        if avg_f1 > best_f1:
+            best_f1 = avg_f1
+            best_params = params.copy()
+        model.stop_spark()
+    return best_params
+
+
+def compute_f1_score(actual, pred, k=10):
+    """F1@k of the top-k predicted ids against the rated ids (als_model.py:171-177)."""
+    actual_items = set(actual.keys())
+    ranked = sorted(pred.items(), key=lambda x: x[1], reverse=True)[:k]
+    pred_items = set(item for item, _ in ranked)
+    tp = len(actual_items & pred_items)
+    precision = tp / k
+    recall = tp / len(actual_items) if actual_items else 0
+    return 2 * (precision * recall) / (precision + recall) if (precision + recall) > 0 else 0

@@ -1,0 +1,102 @@
+"""Host-side plumbing around the ALS kernels: COO -> CSR, row sharding, work plans.
+
+Stands where the reference hands its pandas frame to Spark (src/als_model.py:51) and
+Spark partitions ratings into in-blocks (ALS.scala makeBlocks, behind als_model.py:62).
+torch is used for device memory and sorting only; the arithmetic is in csrc/.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+
+@dataclass
+class CsrShard:
+    """Rows [row_begin, row_end) of a ratings matrix in CSR form on one device."""
+    row_begin: int
+    row_end: int
+    n_rows_total: int
+    rowptr: torch.Tensor        # int64 [rows+1], local offsets (device)
+    colidx: torch.Tensor        # int32 [nnz_local]
+    vals: torch.Tensor          # fp32  [nnz_local]
+    rowptr_host: np.ndarray     # int64 [rows+1]
+
+    @property
+    def n_rows(self):
+        return self.row_end - self.row_begin
+
+    @property
+    def nnz(self):
+        return int(self.colidx.numel())
+
+
+def balanced_row_bounds(counts: np.ndarray, world: int) -> np.ndarray:
+    """Contiguous row ranges with ~equal rating counts (nnz-balanced), one per rank.
+    Returns int64 [world+1]."""
+    n = len(counts)
+    csum = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])
+    total = csum[-1]
+    bounds = np.zeros(world + 1, dtype=np.int64)
+    for r in range(1, world):
+        bounds[r] = np.searchsorted(csum, total * r / world, side="left")
+    bounds[world] = n
+    return np.maximum.accumulate(np.minimum(bounds, n))
+
+
+def build_csr(rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n_rows: int,
+              row_begin: int = 0, row_end: int | None = None) -> CsrShard:
+    """Stable COO -> CSR for rows in [row_begin, row_end): the ratings of a row keep their
+    input order, duplicates are kept (Spark does not merge them)."""
+    if row_end is None:
+        row_end = n_rows
+    dev = rows.device
+    rows = rows.to(torch.int64)
+    if row_begin != 0 or row_end != n_rows:
+        keep = (rows >= row_begin) & (rows < row_end)
+        rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    local = rows - row_begin
+    order = torch.argsort(local, stable=True)
+    counts = torch.bincount(local, minlength=row_end - row_begin)
+    rowptr = torch.zeros(row_end - row_begin + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=rowptr[1:])
+    return CsrShard(row_begin, row_end, n_rows, rowptr, cols[order].to(torch.int32).contiguous(),
+                    vals[order].to(torch.float32).contiguous(), rowptr.cpu().numpy())
+
+
+class AlsPlanHandle:
+    """Owns the device arrays of a hals_als_plan and the matching workspace."""
+
+    def __init__(self, shard: CsrShard, k: int, seg_len: int | None = None, device=None):
+        L = nat.lib()
+        self.k = k
+        self.seg_len = int(seg_len or L.hals_als_default_seg_len(k))
+        rp = np.ascontiguousarray(shard.rowptr_host, dtype=np.int64)
+        m = len(rp) - 1
+        n_items, n_long, n_slots = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        nat.check(L.hals_als_plan_count_host(nat.ptr(rp), m, self.seg_len, ctypes.byref(n_items),
+                                             ctypes.byref(n_long), ctypes.byref(n_slots)), "plan_count")
+        self.n_items, self.n_long, self.n_slots = n_items.value, n_long.value, n_slots.value
+        h = {
+            "item_row": np.empty(max(self.n_items, 1), np.int32),
+            "item_begin": np.empty(max(self.n_items, 1), np.int64),
+            "item_len": np.empty(max(self.n_items, 1), np.int32),
+            "item_slot": np.empty(max(self.n_items, 1), np.int32),
+            "long_row": np.empty(max(self.n_long, 1), np.int32),
+            "long_slot0": np.empty(max(self.n_long, 1), np.int32),
+            "long_nseg": np.empty(max(self.n_long, 1), np.int32),
+        }
+        nat.check(L.hals_als_plan_fill_host(nat.ptr(rp), m, self.seg_len, *(nat.ptr(h[n]) for n in (
+            "item_row", "item_begin", "item_len", "item_slot", "long_row", "long_slot0", "long_nseg"))), "plan_fill")
+        self.host = h
+        dev = device if device is not None else shard.colidx.device
+        self.dev = {n: torch.from_numpy(a).to(dev) for n, a in h.items()}
+        self.struct = nat.AlsPlan(
+            n_items=self.n_items, n_long_rows=self.n_long, n_slots=self.n_slots, seg_len=self.seg_len, reserved=0,
+            **{n: self.dev[n].data_ptr() for n in h})
+        self.workspace_bytes = int(L.hals_als_workspace_bytes(self.n_slots, k))
+        self.workspace = torch.empty(max(self.workspace_bytes, 16), dtype=torch.uint8, device=dev)

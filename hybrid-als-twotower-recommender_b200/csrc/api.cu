@@ -1,0 +1,106 @@
+// C-ABI glue: error state, launch counter, host-side ALS planner, half-step dispatch.
+#include "common.cuh"
+
+namespace hals {
+thread_local char g_last_error[512] = "";
+std::atomic<int64_t> g_launch_count{0};
+
+int als_half_step_simt(const int32_t* colidx, const float* vals, const float* src, float* dst, int k,
+                       float reg, int implicit, float alpha, const float* gram,
+                       const hals_als_plan* plan, float* ws, cudaStream_t st);
+size_t als_slot_floats_host(int k);
+}  // namespace hals
+
+using namespace hals;
+
+static int padded_rank(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : 128; }
+
+extern "C" int hals_abi_version(void) { return HALS_ABI_VERSION; }
+extern "C" const char* hals_last_error(void) { return g_last_error; }
+extern "C" int64_t hals_launch_count(void) { return g_launch_count.load(); }
+extern "C" int hals_max_rank(void) { return 128; }
+
+extern "C" int32_t hals_als_default_seg_len(int k) { return k <= 32 ? 8192 : 4096; }
+
+extern "C" size_t hals_als_workspace_bytes(int64_t n_slots, int k) {
+  const size_t KP = (size_t)padded_rank(k);
+  return (size_t)(n_slots > 0 ? n_slots : 0) * (KP * KP + KP + 4) * sizeof(float) + 16;
+}
+
+// Work items: first every slice of every long row (big, uniform items first so that the
+// tail of the grid is made of short rows), then the remaining non-empty rows in order.
+extern "C" int hals_als_plan_count_host(const int64_t* rowptr_host, int64_t m, int32_t seg_len,
+                                        int64_t* n_items, int64_t* n_long_rows, int64_t* n_slots) {
+  HALS_REQUIRE(rowptr_host && n_items && n_long_rows && n_slots, "null pointer");
+  HALS_REQUIRE(seg_len >= 32 && m >= 0, "seg_len must be >= 32");
+  int64_t items = 0, longs = 0, slots = 0;
+  for (int64_t j = 0; j < m; ++j) {
+    const int64_t len = rowptr_host[j + 1] - rowptr_host[j];
+    if (len < 0) return fail(HALS_ERR_INVALID, "%s: rowptr not monotone%s", __func__);
+    if (len == 0) continue;
+    if (len > seg_len) {
+      const int64_t ns = (len + seg_len - 1) / seg_len;
+      items += ns; slots += ns; ++longs;
+    } else {
+      ++items;
+    }
+  }
+  *n_items = items; *n_long_rows = longs; *n_slots = slots;
+  return 0;
+}
+
+extern "C" int hals_als_plan_fill_host(const int64_t* rowptr_host, int64_t m, int32_t seg_len,
+                                       int32_t* item_row, int64_t* item_begin, int32_t* item_len,
+                                       int32_t* item_slot, int32_t* long_row, int32_t* long_slot0,
+                                       int32_t* long_nseg) {
+  HALS_REQUIRE(rowptr_host && item_row && item_begin && item_len && item_slot, "null pointer");
+  HALS_REQUIRE(seg_len >= 32, "seg_len must be >= 32");
+  int64_t it = 0, lr = 0, slot = 0;
+  for (int64_t j = 0; j < m; ++j) {  // pass 1: long rows
+    const int64_t b = rowptr_host[j], len = rowptr_host[j + 1] - b;
+    if (len <= seg_len) continue;
+    HALS_REQUIRE(long_row && long_slot0 && long_nseg, "null long-row arrays");
+    const int64_t ns = (len + seg_len - 1) / seg_len;
+    // equal slices (not seg_len + remainder) so that slice costs are uniform
+    const int64_t per = (len + ns - 1) / ns;
+    long_row[lr] = (int32_t)j; long_slot0[lr] = (int32_t)slot; long_nseg[lr] = (int32_t)ns; ++lr;
+    for (int64_t s = 0; s < ns; ++s) {
+      const int64_t o = s * per;
+      const int64_t l = (o + per <= len) ? per : len - o;
+      item_row[it] = (int32_t)j; item_begin[it] = b + o; item_len[it] = (int32_t)l;
+      item_slot[it] = (int32_t)slot; ++it; ++slot;
+    }
+  }
+  for (int64_t j = 0; j < m; ++j) {  // pass 2: whole rows
+    const int64_t b = rowptr_host[j], len = rowptr_host[j + 1] - b;
+    if (len == 0 || len > seg_len) continue;
+    item_row[it] = (int32_t)j; item_begin[it] = b; item_len[it] = (int32_t)len; item_slot[it] = -1; ++it;
+  }
+  return 0;
+}
+
+extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, const float* vals,
+                                  int64_t m_dst, const float* src, int64_t n_src, float* dst, int k,
+                                  float reg, int implicit, float alpha, const float* gram,
+                                  const hals_als_plan* plan, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  (void)rowptr; (void)n_src;
+  HALS_REQUIRE(plan != nullptr, "null plan");
+  HALS_REQUIRE(k >= 1 && k <= 128, "rank must be in [1,128]");
+  HALS_REQUIRE(m_dst >= 0, "negative row count");
+  HALS_REQUIRE(!implicit || gram != nullptr, "implicit mode needs the Gram matrix");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m_dst == 0) return 0;
+  HALS_REQUIRE(dst != nullptr, "null dst");
+  // rows without ratings are absent from the Spark model; they are kept as zero rows
+  HALS_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)m_dst * k, st));
+  if (plan->n_items == 0) return 0;
+  HALS_REQUIRE(colidx && vals && src, "null pointer");
+  HALS_REQUIRE(plan->item_row && plan->item_begin && plan->item_len && plan->item_slot, "null plan arrays");
+  if (plan->n_slots > 0) {
+    HALS_REQUIRE(workspace != nullptr, "null workspace");
+    if (workspace_bytes < hals_als_workspace_bytes(plan->n_slots, k))
+      return fail(HALS_ERR_WORKSPACE, "%s: workspace too small%s", __func__);
+  }
+  return als_half_step_simt(colidx, vals, src, dst, k, reg, implicit, alpha, gram, plan, (float*)workspace, st);
+}

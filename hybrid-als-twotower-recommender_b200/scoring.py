@@ -1,0 +1,114 @@
+"""Batched hybrid scoring on B200: replaces the reference's per-user loop of
+ALSModel.predict_for_user + TwoTowerModel.predict_for_user + adaptive_fusion + sorted()[:k]
+(src/hybrid_system.py:95-116) with two fused passes over an item shard:
+
+  pass 1  hals_score_extrema     per-user (min,max) of both models      [+ min/max all-reduce]
+  pass 2  hals_score_blend_topk  blend + per-user top-k, scores never stored
+          [+ all-to-all of the per-shard lists and hals_topk_merge when item-sharded]
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as nat
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+def fusion_weights(als_f1: float, tt_f1: float):
+    """src/hybrid_system.py:69 -- strict '>'."""
+    return (0.8, 0.2) if als_f1 > tt_f1 else (0.2, 0.8)
+
+
+def merge_lists(part_idx: torch.Tensor, part_score: torch.Tensor):
+    """[P, U, k] partial lists -> [U, k] (score desc, index asc)."""
+    L = nat.lib()
+    P, U, k = part_idx.shape
+    out_idx = torch.empty((U, k), dtype=torch.int32, device=part_idx.device)
+    out_score = torch.empty((U, k), dtype=torch.float32, device=part_idx.device)
+    nat.check(L.hals_topk_merge(nat.ptr(part_idx.contiguous()), nat.ptr(part_score.contiguous()), P, U, k,
+                                nat.ptr(out_idx), nat.ptr(out_score), nat.current_stream()), "hals_topk_merge")
+    return out_idx, out_score
+
+
+class HybridScorer:
+    """Holds the four operand matrices of one item shard in HBM (fp32, row-major)."""
+
+    def __init__(self, Ua, Ia, Ut, It, item_offset: int = 0, dist_rank: int = 0, world: int = 1):
+        self.Ua, self.Ia, self.Ut, self.It = (None if t is None else t.contiguous() for t in (Ua, Ia, Ut, It))
+        ref_u = self.Ua if self.Ua is not None else self.Ut
+        ref_i = self.Ia if self.Ia is not None else self.It
+        self.n_users, self.n_items = int(ref_u.shape[0]), int(ref_i.shape[0])
+        self.ka = 0 if self.Ua is None else int(self.Ua.shape[1])
+        self.kt = 0 if self.Ut is None else int(self.Ut.shape[1])
+        self.device = ref_u.device
+        self.item_offset, self.rank, self.world = int(item_offset), dist_rank, world
+        self._ws = None
+
+    def _ops(self, u0, u1):
+        def sl(t):
+            return (None, 0) if t is None else (nat.ptr(t[u0:u1]), t.stride(0))
+        (ua, uas), (ut, uts) = sl(self.Ua), sl(self.Ut)
+        ia = (None, 0) if self.Ia is None else (nat.ptr(self.Ia), self.Ia.stride(0))
+        it = (None, 0) if self.It is None else (nat.ptr(self.It), self.It.stride(0))
+        return ua, uas, ia[0], ia[1], self.ka, ut, uts, it[0], it[1], self.kt
+
+    def extrema(self, u0: int = 0, u1: int | None = None) -> torch.Tensor:
+        """[U,4] = (min_als, max_als, min_tt, max_tt) per user over ALL items (all shards)."""
+        L = nat.lib()
+        u1 = self.n_users if u1 is None else u1
+        ex = torch.empty((u1 - u0, 4), dtype=torch.float32, device=self.device)
+        nat.check(L.hals_score_extrema(*self._ops(u0, u1), u1 - u0, self.n_items, nat.ptr(ex),
+                                       nat.current_stream()), "hals_score_extrema")
+        dist = _dist()
+        if dist is not None and self.world > 1:
+            sign = torch.tensor([-1.0, 1.0, -1.0, 1.0], device=self.device)
+            ex *= sign                                  # min -> max of the negation: one MAX all-reduce
+            dist.all_reduce(ex, op=dist.ReduceOp.MAX)
+            ex *= sign
+        return ex
+
+    def topk_local(self, extrema, k, w_als, w_tt, u0=0, u1=None):
+        """Top-k of this item shard only (global item numbering via item_offset)."""
+        L = nat.lib()
+        u1 = self.n_users if u1 is None else u1
+        n = u1 - u0
+        need = int(L.hals_score_workspace_bytes(n, self.n_items, self.ka, self.kt, k))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        idx = torch.empty((n, k), dtype=torch.int32, device=self.device)
+        sc = torch.empty((n, k), dtype=torch.float32, device=self.device)
+        nat.check(L.hals_score_blend_topk(*self._ops(u0, u1), n, self.n_items, nat.ptr(extrema), float(w_als),
+                                          float(w_tt), int(k), self.item_offset, nat.ptr(idx), nat.ptr(sc),
+                                          nat.ptr(self._ws), self._ws.numel(), nat.current_stream()),
+                  "hals_score_blend_topk")
+        return idx, sc
+
+    def recommend(self, k: int, w_als: float, w_tt: float, u0: int = 0, u1: int | None = None):
+        """Final top-k for users [u0,u1).  Item-sharded runs return, on every rank, the merged
+        lists of ITS slice of those users (rank r owns the r-th equal chunk) -- see
+        `user_slice`."""
+        u1 = self.n_users if u1 is None else u1
+        ex = self.extrema(u0, u1)
+        idx, sc = self.topk_local(ex, k, w_als, w_tt, u0, u1)
+        dist = _dist()
+        if dist is None or self.world == 1:
+            return idx, sc
+        n = u1 - u0
+        per = (n + self.world - 1) // self.world
+        pad = per * self.world - n
+        if pad:
+            idx = torch.cat([idx, torch.full((pad, k), -1, dtype=idx.dtype, device=idx.device)])
+            sc = torch.cat([sc, torch.full((pad, k), float("-inf"), dtype=sc.dtype, device=sc.device)])
+        ridx, rsc = torch.empty_like(idx), torch.empty_like(sc)
+        dist.all_to_all_single(ridx, idx)     # chunk j of my lists -> rank j
+        dist.all_to_all_single(rsc, sc)
+        return merge_lists(ridx.view(self.world, per, k), rsc.view(self.world, per, k))
+
+    def user_slice(self, u0, u1):
+        n = u1 - u0
+        per = (n + self.world - 1) // self.world
+        return u0 + self.rank * per, min(u1, u0 + (self.rank + 1) * per)

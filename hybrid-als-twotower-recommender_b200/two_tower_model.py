@@ -1,0 +1,268 @@
+"""TwoTowerModel -- drop-in for the reference's src/two_tower_model.py (class at :17-167).
+
+Same constructor, attributes and method names.  The forward pass that the reference runs
+through Keras `Model.predict` (two_tower_model.py:145) is evaluated by the tower kernels of
+libhals_b200.so: hals_tower_item / hals_tower_user precompute the tower outputs once per id
+(the reference recomputes the item tower for every user) and hals_score_one_user takes the
+dot products.  `self.model` is a TowerWeights holder instead of a keras.Model.
+
+Training (two_tower_model.py:91-121) is outside the north-star path; `train` is kept so the
+class stays usable end to end and runs a plain torch Adam/MSE loop over the same graph.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+from sklearn.preprocessing import MinMaxScaler
+
+LN_EPS = 1e-3  # Keras LayerNormalization default epsilon
+
+
+class TowerParams:
+    """Weights of the graph built at two_tower_model.py:38-89, as fp32 device tensors."""
+    NAMES = ("user_emb", "item_emb", "manu_emb", "cat_emb", "num_w", "num_b", "out_w", "out_b",
+             "user_ln_g", "user_ln_b", "item_ln_g", "item_ln_b")
+
+    def __init__(self, tensors: dict, embedding_size: int):
+        self.t = tensors
+        self.embedding_size = int(embedding_size)
+
+    @classmethod
+    def keras_init(cls, num_users, num_items, num_manufacturers, num_categories, embedding_size, device, seed=0):
+        """Keras default initialisers: Embedding U(-0.05,0.05); Dense Glorot-uniform, zero bias;
+        LayerNormalization gamma=1, beta=0."""
+        import torch
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        E = embedding_size
+
+        def emb(n, d):
+            return (torch.rand((n, d), generator=g) * 0.1 - 0.05)
+
+        def glorot(i, o):
+            lim = (6.0 / (i + o)) ** 0.5
+            return (torch.rand((i, o), generator=g) * 2 - 1) * lim
+
+        t = {
+            "user_emb": emb(num_users, E), "item_emb": emb(num_items, E),
+            "manu_emb": emb(num_manufacturers, 8), "cat_emb": emb(num_categories, 8),
+            "num_w": glorot(2, 16), "num_b": torch.zeros(16),
+            "out_w": glorot(E + 8 + 8 + 16, E), "out_b": torch.zeros(E),
+            "user_ln_g": torch.ones(E), "user_ln_b": torch.zeros(E),
+            "item_ln_g": torch.ones(E), "item_ln_b": torch.zeros(E),
+        }
+        return cls({k: v.float().contiguous().to(device) for k, v in t.items()}, E)
+
+    @classmethod
+    def from_numpy(cls, arrays: dict, device):
+        import torch
+        t = {k: torch.from_numpy(np.ascontiguousarray(arrays[k], dtype=np.float32)).to(device) for k in cls.NAMES}
+        return cls(t, t["user_emb"].shape[1])
+
+    def to_numpy(self):
+        return {k: v.detach().cpu().numpy() for k, v in self.t.items()}
+
+    def struct(self, scaler):
+        from . import _native as nat
+        w = nat.TowerWeights()
+        w.embedding_size = self.embedding_size
+        w.manu_dim = int(self.t["manu_emb"].shape[1])
+        w.cat_dim = int(self.t["cat_emb"].shape[1])
+        w.num_hidden = int(self.t["num_b"].shape[0])
+        for k in self.NAMES:
+            setattr(w, k, self.t[k].data_ptr())
+        w.ln_eps = LN_EPS
+        if scaler is not None and hasattr(scaler, "scale_"):
+            sc, mn = scaler.scale_, scaler.min_
+        else:
+            sc, mn = (1.0, 1.0), (0.0, 0.0)
+        w.num_scale[0], w.num_scale[1] = float(sc[0]), float(sc[1])
+        w.num_offset[0], w.num_offset[1] = float(mn[0]), float(mn[1])
+        return w
+
+
+class TwoTowerModel:
+    """
+    Two-Tower Model Architecture (reference docstring, two_tower_model.py:18-23)
+    - User Tower: userId embedding
+    - Item Tower: itemId + manufacturer + category + numeric features
+    - Dot product similarity with layer normalization
+    """
+
+    def __init__(self, num_users, num_items, num_manufacturers, num_categories,
+                 embedding_size=50, learning_rate=0.001):
+        self.num_users = num_users
+        self.num_items = num_items
+        self.num_manufacturers = num_manufacturers
+        self.num_categories = num_categories
+        self.embedding_size = embedding_size
+        self.learning_rate = learning_rate
+        self.model = None
+        self.scaler = MinMaxScaler()
+        self.is_trained = False
+
+    # -- graph --------------------------------------------------------------------------------
+    def build_model(self, seed=0):
+        import torch
+        from . import _native as nat
+        nat.lib()
+        nat.require_cuda()
+        self.model = TowerParams.keras_init(self.num_users, self.num_items, self.num_manufacturers,
+                                            self.num_categories, self.embedding_size, torch.device("cuda"), seed)
+        return self.model
+
+    def _prepare_features(self, data):
+        """Feature preprocessing (two_tower_model.py:123-134); the scaler is re-fitted here, as in
+        the reference (`fit_transform`, :133)."""
+        if data is None:
+            return None
+        return {
+            "user_in": data["userId"].values,
+            "item_id_in": data["itemId"].values,
+            "manufacturer_in": data["manufacturer_id"].values,
+            "category_in": data["category_id"].values,
+            "numeric_in": self.scaler.fit_transform(data[["price", "average_review_rating"]]),
+        }
+
+    # -- forward (the hot path) -----------------------------------------------------------------
+    def item_vectors(self, item_features, out=None):
+        """Item tower outputs [n, E] (device) for the rows of a DataFrame with the columns
+        itemId, manufacturer_id, category_id, price, average_review_rating."""
+        import torch
+        from . import _native as nat
+        dev = self.model.t["item_emb"].device
+        n = len(item_features)
+
+        def col(name):
+            return torch.from_numpy(np.ascontiguousarray(item_features[name].values, dtype=np.int32)).to(dev)
+
+        ids, manu, cat = col("itemId"), col("manufacturer_id"), col("category_id")
+        num = torch.from_numpy(np.ascontiguousarray(
+            item_features[["price", "average_review_rating"]].values, dtype=np.float32)).to(dev)
+        if out is None:
+            out = torch.empty((n, self.embedding_size), dtype=torch.float32, device=dev)
+        w = self.model.struct(self.scaler)
+        nat.check(nat.lib().hals_tower_item(w, nat.ptr(ids), nat.ptr(manu), nat.ptr(cat), nat.ptr(num), n,
+                                            nat.ptr(out), out.stride(0), nat.current_stream()), "hals_tower_item")
+        return out
+
+    def user_vectors(self, user_ids, out=None):
+        import torch
+        from . import _native as nat
+        dev = self.model.t["user_emb"].device
+        ids = torch.from_numpy(np.ascontiguousarray(np.asarray(user_ids), dtype=np.int32)).to(dev)
+        if out is None:
+            out = torch.empty((ids.numel(), self.embedding_size), dtype=torch.float32, device=dev)
+        w = self.model.struct(self.scaler)
+        nat.check(nat.lib().hals_tower_user(w, nat.ptr(ids), ids.numel(), nat.ptr(out), out.stride(0),
+                                            nat.current_stream()), "hals_tower_user")
+        return out
+
+    def predict_for_user(self, user_id, item_features):
+        """Scores of one user against every row of `item_features` (two_tower_model.py:136-146)."""
+        import torch
+        from . import _native as nat
+        iv = self.item_vectors(item_features)
+        uv = self.user_vectors([user_id])
+        out = torch.empty(iv.shape[0], dtype=torch.float32, device=iv.device)
+        nat.check(nat.lib().hals_score_one_user(nat.ptr(uv), nat.ptr(iv), iv.stride(0), self.embedding_size, None,
+                                                iv.shape[0], nat.ptr(out), nat.current_stream()),
+                  "hals_score_one_user")
+        predictions = out.cpu().numpy()
+        return list(zip(item_features["itemId"], predictions.flatten()))
+
+    # -- training (outside the north-star path; plain torch) ----------------------------------------
+    def _torch_forward(self, p, f, dev):
+        import torch
+        import torch.nn.functional as F
+        E = self.embedding_size
+        u = F.layer_norm(p["user_emb"][torch.as_tensor(f["user_in"], device=dev).long()], (E,),
+                         p["user_ln_g"], p["user_ln_b"], LN_EPS)
+        num = torch.as_tensor(np.asarray(f["numeric_in"], dtype=np.float32), device=dev)
+        h = torch.relu(num @ p["num_w"] + p["num_b"])
+        cat = torch.cat([p["item_emb"][torch.as_tensor(f["item_id_in"], device=dev).long()],
+                         p["manu_emb"][torch.as_tensor(f["manufacturer_in"], device=dev).long()],
+                         p["cat_emb"][torch.as_tensor(f["category_in"], device=dev).long()], h], dim=1)
+        i = F.layer_norm(cat @ p["out_w"] + p["out_b"], (E,), p["item_ln_g"], p["item_ln_b"], LN_EPS)
+        return (u * i).sum(dim=1)
+
+    def train(self, train_data, val_data=None, batch_size=256, epochs=10):
+        """Adam(lr) on MSE with EarlyStopping(patience=3, restore_best_weights) when validation data
+        is given (two_tower_model.py:91-121).  Returns a dict of per-epoch losses."""
+        import torch
+        if self.model is None:
+            self.build_model()
+        dev = self.model.t["user_emb"].device
+        params = {k: v.clone().requires_grad_(True) for k, v in self.model.t.items()}
+        opt = torch.optim.Adam(list(params.values()), lr=self.learning_rate, eps=1e-7)
+        tf = self._prepare_features(train_data)
+        y = torch.as_tensor(train_data["average_review_rating"].values.astype(np.float32), device=dev)
+        has_val = val_data is not None and len(val_data) > 0
+        vf = self._prepare_features(val_data) if has_val else None
+        vy = torch.as_tensor(val_data["average_review_rating"].values.astype(np.float32), device=dev) if has_val else None
+        if has_val:  # _prepare_features re-fits the scaler (reference behaviour); keep the train fit for predict
+            tf = self._prepare_features(train_data)
+        n = len(train_data)
+        history = {"loss": [], "val_loss": []}
+        best, best_state, bad = float("inf"), None, 0
+        g = torch.Generator(device="cpu").manual_seed(0)
+        for _ in range(int(epochs)):
+            perm = torch.randperm(n, generator=g).numpy()
+            tot = 0.0
+            for s in range(0, n, batch_size):
+                b = perm[s:s + batch_size]
+                fb = {k: np.asarray(v)[b] for k, v in tf.items()}
+                loss = ((self._torch_forward(params, fb, dev) - y[torch.as_tensor(b, device=dev)]) ** 2).mean()
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                tot += float(loss) * len(b)
+            history["loss"].append(tot / max(n, 1))
+            if has_val:
+                with torch.no_grad():
+                    vl = float(((self._torch_forward(params, vf, dev) - vy) ** 2).mean())
+                history["val_loss"].append(vl)
+                if vl < best:
+                    best, bad = vl, 0
+                    best_state = {k: v.detach().clone() for k, v in params.items()}
+                else:
+                    bad += 1
+                    if bad >= 3:
+                        break
+        final = best_state if best_state is not None else {k: v.detach() for k, v in params.items()}
+        self.model = TowerParams({k: v.contiguous() for k, v in final.items()}, self.embedding_size)
+        self.is_trained = True
+        return history
+
+    # -- persistence ------------------------------------------------------------------------------
+    def save_model(self, model_path="models/twotower.keras"):
+        os.makedirs(os.path.dirname(model_path) or ".", exist_ok=True)
+        with open(model_path, "wb") as f:
+            np.savez(f, embedding_size=self.embedding_size, **self.model.to_numpy())
+        with open(f"{model_path}_scaler.pkl", "wb") as f:
+            pickle.dump(self.scaler, f)
+
+    @classmethod
+    def load_model(cls, model_path="models/twotower.keras"):
+        import torch
+        from . import _native as nat
+        nat.lib()
+        nat.require_cuda()
+        z = np.load(model_path)
+        with open(f"{model_path}_scaler.pkl", "rb") as f:
+            scaler = pickle.load(f)
+        params = TowerParams.from_numpy({k: z[k] for k in TowerParams.NAMES}, torch.device("cuda"))
+        loaded_model = cls(params.t["user_emb"].shape[0], params.t["item_emb"].shape[0],
+                           params.t["manu_emb"].shape[0], params.t["cat_emb"].shape[0],
+                           embedding_size=params.embedding_size)
+        loaded_model.model = params
+        loaded_model.scaler = scaler
+        loaded_model.is_trained = True
+        return loaded_model
+
+
+def compute_f1_score(actual, pred, k=10):
+    """two_tower_model.py:238-245 (same function as als_model.compute_f1_score)."""
+    from .als_model import compute_f1_score as f
+    return f(actual, pred, k)
