@@ -35,8 +35,8 @@ struct AlsTile {
 
 template <int KP>
 struct AlsSmem {
-  float A[(KP + 1) * AlsTile<KP>::LD];          // k x k normal matrix + rhs row (row KP)
-  float G[2][kAlsChunk * KP];                   // gathered source rows, double buffered
+  float A[((KP + 1) * AlsTile<KP>::LD + 3) / 4 * 4];  // k x k normal matrix + rhs row (row KP), 16B multiple
+  alignas(16) float G[2][kAlsChunk * KP];                   // gathered source rows, double buffered
   int idx[3][kAlsChunk];
   float wa[3][kAlsChunk];                       // weight of y y^T
   float wb[3][kAlsChunk];                       // weight of y in b
@@ -156,7 +156,7 @@ als_build_solve_kernel(const int32_t* __restrict__ colidx, const float* __restri
         counted = true;
       }
       const int st = c % 3;
-      sm.idx[st][tid] = ci;
+      sm.idx[st][tid] = ok ? ci : -1;   // -1: the gather zero-fills this row
       sm.wa[st][tid] = ok ? wa : 0.f;
       sm.wb[st][tid] = ok ? wb : 0.f;
       npos += __popc(__ballot_sync(0xffffffffu, ok && counted));
@@ -169,12 +169,14 @@ als_build_solve_kernel(const int32_t* __restrict__ colidx, const float* __restri
       const int k4 = k >> 2;
       for (int q = tid; q < T * k4; q += kAlsThreads) {
         const int t = q / k4, c4 = q - t * k4;
-        cp_async16(G + t * KP + c4 * 4, src + (int64_t)sm.idx[st][t] * k + c4 * 4);
+        const int ci = sm.idx[st][t];
+        cp_async16(G + t * KP + c4 * 4, src + (int64_t)(ci < 0 ? 0 : ci) * k + c4 * 4, ci >= 0);
       }
     } else {
       for (int q = tid; q < T * k; q += kAlsThreads) {
         const int t = q / k, f = q - t * k;
-        cp_async4(G + t * KP + f, src + (int64_t)sm.idx[st][t] * k + f);
+        const int ci = sm.idx[st][t];
+        cp_async4(G + t * KP + f, src + (int64_t)(ci < 0 ? 0 : ci) * k + f, ci >= 0);
       }
     }
   };

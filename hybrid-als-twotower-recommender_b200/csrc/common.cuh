@@ -69,13 +69,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+// `valid == false` zero-fills the destination (src-size 0: nothing is read from global)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid = true) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(valid ? 16 : 0));
 }
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, bool valid = true) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(valid ? 4 : 0));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
