@@ -69,6 +69,8 @@ SIGNATURES = {
     "hals_topk_merge": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp, c_vp]),
     "hals_score_one_user": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_i64, c_vp, c_vp]),
     "hals_fuse_lists": (ctypes.c_int, [c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp]),
+    "hals_debug_umma_probe": (ctypes.c_int, [c_vp, ctypes.c_int] + [ctypes.c_uint32] * 8 +
+                              [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
 }
 
 _lib = None

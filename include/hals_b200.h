@@ -200,6 +200,15 @@ int hals_score_one_user(const float* u, const float* V, int64_t v_stride, int k,
 int hals_fuse_lists(const float* als, const float* tt, int64_t n, float w_als, float w_tt, float* out,
                     float* scratch4, void* stream);
 
+/* Self-test of the tcgen05 (UMMA) operand layouts: copies a caller-built shared-memory image,
+ * issues n_mma tcgen05.mma instructions (M=128) with the given descriptor fields and returns
+ * the TMEM accumulator as out[128][ncols].  Used only by tests/test_gpu_umma.py to pin the
+ * layouts the tensor-core kernels rely on. */
+int hals_debug_umma_probe(const void* img, int img_bytes, uint32_t a_off, uint32_t b_off, uint32_t a_lbo,
+                          uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t swizzle, uint32_t idesc,
+                          int n_mma, uint32_t a_step, uint32_t b_step, int kind_tf32, int ncols, float* out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif
