@@ -92,8 +92,8 @@ class AlsEngine:
         self.Rt = build_csr(items, users, ratings, n_items, ib, ie)      # item rows -> user columns
         self.plan_R = self.plan_Rt = None
         if make_plans:
-            self.plan_R = AlsPlanHandle(self.R, self.k, seg_len)
-            self.plan_Rt = AlsPlanHandle(self.Rt, self.k, seg_len)
+            self.plan_R = AlsPlanHandle(self.R, self.k, seg_len, n_src=n_items)
+            self.plan_Rt = AlsPlanHandle(self.Rt, self.k, seg_len, n_src=n_users)
         self.X = torch.zeros((n_users, self.k), dtype=torch.float32, device=self.device)
         self.Y = torch.zeros((n_items, self.k), dtype=torch.float32, device=self.device)
         self.gram = None

@@ -71,7 +71,7 @@ def build_csr(rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n_rows
 class AlsPlanHandle:
     """Owns the device arrays of a hals_als_plan and the matching workspace."""
 
-    def __init__(self, shard: CsrShard, k: int, seg_len: int | None = None, device=None):
+    def __init__(self, shard: CsrShard, k: int, seg_len: int | None = None, device=None, n_src: int = 0):
         L = nat.lib()
         self.k = k
         self.seg_len = int(seg_len or L.hals_als_default_seg_len(k))
@@ -98,5 +98,5 @@ class AlsPlanHandle:
         self.struct = nat.AlsPlan(
             n_items=self.n_items, n_long_rows=self.n_long, n_slots=self.n_slots, seg_len=self.seg_len, reserved=0,
             **{n: self.dev[n].data_ptr() for n in h})
-        self.workspace_bytes = int(L.hals_als_workspace_bytes(self.n_slots, k))
+        self.workspace_bytes = int(L.hals_als_workspace_bytes(self.n_slots, k, int(n_src)))
         self.workspace = torch.empty(max(self.workspace_bytes, 16), dtype=torch.uint8, device=dev)

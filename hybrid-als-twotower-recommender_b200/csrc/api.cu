@@ -1,4 +1,6 @@
 // C-ABI glue: error state, launch counter, host-side ALS planner, half-step dispatch.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hals {
@@ -8,7 +10,8 @@ std::atomic<int64_t> g_launch_count{0};
 int als_half_step_simt(const int32_t* colidx, const float* vals, const float* src, float* dst, int k,
                        float reg, int implicit, float alpha, const float* gram,
                        const hals_als_plan* plan, float* ws, cudaStream_t st);
-size_t als_slot_floats_host(int k);
+int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* src, int64_t n_src, float* dst,
+                       float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
 }  // namespace hals
 
 using namespace hals;
@@ -22,9 +25,19 @@ extern "C" int hals_max_rank(void) { return 128; }
 
 extern "C" int32_t hals_als_default_seg_len(int k) { return k <= 32 ? 8192 : 4096; }
 
-extern "C" size_t hals_als_workspace_bytes(int64_t n_slots, int k) {
+static size_t slot_region_bytes(int64_t n_slots, int k) {
   const size_t KP = (size_t)padded_rank(k);
-  return (size_t)(n_slots > 0 ? n_slots : 0) * (KP * KP + KP + 4) * sizeof(float) + 16;
+  return (size_t)(n_slots > 0 ? n_slots : 0) * (KP * KP + KP + 4) * sizeof(float);
+}
+// tensor-core path: explicit feedback, rank 64 (HALS_FORCE_SIMT=1 routes everything to the SIMT path)
+static bool use_tc(int k, int implicit) {
+  static const bool force_simt = [] { const char* e = getenv("HALS_FORCE_SIMT"); return e && e[0] == '1'; }();
+  return !force_simt && !implicit && k == 64;
+}
+
+extern "C" size_t hals_als_workspace_bytes(int64_t n_slots, int k, int64_t n_src) {
+  // [partial (A,b,n) slots][bf16 h|l split of the source factors, tensor-core path]
+  return slot_region_bytes(n_slots, k) + (size_t)(n_src > 0 ? n_src : 0) * 4 * (size_t)k + 256;
 }
 
 // Work items: first every slice of every long row (big, uniform items first so that the
@@ -84,7 +97,7 @@ extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, 
                                   float reg, int implicit, float alpha, const float* gram,
                                   const hals_als_plan* plan, void* workspace, size_t workspace_bytes,
                                   void* stream) {
-  (void)rowptr; (void)n_src;
+  (void)rowptr;
   HALS_REQUIRE(plan != nullptr, "null plan");
   HALS_REQUIRE(k >= 1 && k <= 128, "rank must be in [1,128]");
   HALS_REQUIRE(m_dst >= 0, "negative row count");
@@ -97,10 +110,13 @@ extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, 
   if (plan->n_items == 0) return 0;
   HALS_REQUIRE(colidx && vals && src, "null pointer");
   HALS_REQUIRE(plan->item_row && plan->item_begin && plan->item_len && plan->item_slot, "null plan arrays");
-  if (plan->n_slots > 0) {
-    HALS_REQUIRE(workspace != nullptr, "null workspace");
-    if (workspace_bytes < hals_als_workspace_bytes(plan->n_slots, k))
-      return fail(HALS_ERR_WORKSPACE, "%s: workspace too small%s", __func__);
+  HALS_REQUIRE(workspace != nullptr, "null workspace");
+  if (workspace_bytes < hals_als_workspace_bytes(plan->n_slots, k, n_src))
+    return fail(HALS_ERR_WORKSPACE, "%s: workspace too small%s", __func__);
+  HALS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
+  if (use_tc(k, implicit)) {
+    void* split = reinterpret_cast<uint8_t*>(workspace) + slot_region_bytes(plan->n_slots, k);
+    return als_half_step_tc64(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
   }
   return als_half_step_simt(colidx, vals, src, dst, k, reg, implicit, alpha, gram, plan, (float*)workspace, st);
 }

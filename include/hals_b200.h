@@ -82,8 +82,9 @@ int hals_als_plan_fill_host(const int64_t* rowptr_host, int64_t m, int32_t seg_l
                             int32_t* item_row, int64_t* item_begin, int32_t* item_len,
                             int32_t* item_slot, int32_t* long_row, int32_t* long_slot0,
                             int32_t* long_nseg);
-/* Bytes of device workspace hals_als_half_step needs for a plan with n_slots slots. */
-size_t hals_als_workspace_bytes(int64_t n_slots, int k);
+/* Bytes of device workspace hals_als_half_step needs for a plan with n_slots slots and a
+ * source factor matrix of n_src rows (the tensor-core path keeps a bf16 split copy of it). */
+size_t hals_als_workspace_bytes(int64_t n_slots, int k, int64_t n_src);
 /* Default segment length for rank k (ratings per work item). */
 int32_t hals_als_default_seg_len(int k);
 

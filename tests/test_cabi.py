@@ -73,9 +73,10 @@ def test_planner_rejects_bad_input():
 
 def test_workspace_queries():
     L = nat.lib()
-    assert L.hals_als_workspace_bytes(0, 64) < 64
-    assert L.hals_als_workspace_bytes(3, 64) >= 3 * (64 * 64 + 64) * 4
-    assert L.hals_als_workspace_bytes(3, 10) >= 3 * (16 * 16 + 16) * 4
+    assert L.hals_als_workspace_bytes(0, 64, 0) <= 256
+    assert L.hals_als_workspace_bytes(3, 64, 0) >= 3 * (64 * 64 + 64) * 4
+    assert L.hals_als_workspace_bytes(3, 10, 0) >= 3 * (16 * 16 + 16) * 4
+    assert L.hals_als_workspace_bytes(0, 64, 1000) >= 1000 * 64 * 4
     assert L.hals_gram_workspace_bytes(128) >= 128 * 128 * 4
     assert L.hals_max_rank() == 128
 

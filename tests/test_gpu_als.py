@@ -30,7 +30,7 @@ def gpu_half_step(rows, cols, vals, n_rows, src, reg, implicit=False, alpha=1.0,
     shard = csr.build_csr(torch.as_tensor(rows).to(dev), torch.as_tensor(cols).to(dev),
                           torch.as_tensor(vals).to(dev), n_rows)
     k = src.shape[1]
-    plan = csr.AlsPlanHandle(shard, k, seg_len)
+    plan = csr.AlsPlanHandle(shard, k, seg_len, n_src=src.shape[0])
     s = torch.from_numpy(np.ascontiguousarray(src)).to(dev)
     dst = torch.full((n_rows, k), 7.0, dtype=torch.float32, device=dev)   # poison: rows must be overwritten
     gram = None
