@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=1_500_000, help="ratings per half-step in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -263,7 +264,7 @@ def main():
     e2e_ms = []
     hX = torch.empty((w["users"], w["rank"]), dtype=torch.float32).pin_memory()
     hY = torch.empty((w["items"], w["rank"]), dtype=torch.float32).pin_memory()
-    for s in range(1 + args.e2e_steps):
+    for s in range(0 if args.no_e2e else 1 + args.e2e_steps):
         barrier()
         t0 = time.perf_counter()
         du, di, dr = hu.to(dev, non_blocking=True), hi.to(dev, non_blocking=True), hr.to(dev, non_blocking=True)
@@ -275,7 +276,7 @@ def main():
         if s > 0:
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
         del e
-    te = torch.tensor([float(np.mean(e2e_ms))], device=dev, dtype=torch.float64)
+    te = torch.tensor([float(np.mean(e2e_ms)) if e2e_ms else float("nan")], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = args.e2e_sweeps * w["nnz"] / (float(te) * 1e-3)

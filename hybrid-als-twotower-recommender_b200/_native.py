@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhals_b200.so")
+LIB_PATH = os.environ.get("HALS_LIB_PATH") or os.path.join(_HERE, "libhals_b200.so")   # env override: A/B builds
 CSRC = os.path.join(_HERE, "csrc")
 
 c_i32, c_i64, c_f32, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t

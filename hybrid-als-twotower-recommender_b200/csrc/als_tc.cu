@@ -20,6 +20,8 @@
 // while one CTA factorises a row (CUDA cores) the others keep the gather/tensor pipes busy.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "als_common.cuh"
 #include "umma.cuh"
 
@@ -34,7 +36,8 @@ constexpr int kTcRowBytes = 128;   // one 64-wide bf16 MN atom row
 constexpr int kTcBlk = kTcKC * kTcRowBytes;          // 4096: one [KC][64] block
 constexpr int kTcStageBytes = 3 * kTcBlk;            // H | L | R
 constexpr int kTcLD = kTcK + 1;
-constexpr int kTcS1Floats = ((kTcK + 1) * kTcLD + 3) / 4 * 4;
+constexpr int kTcLDP = 68;                            // published pivot rows: 16-byte aligned rows
+constexpr int kTcS1Floats = 65 * kTcLDP;
 constexpr int kTcTmemCols = 128;
 constexpr int kTcN = 80;
 
@@ -60,24 +63,219 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t n_rows,
   *reinterpret_cast<uint4*>(o + k + c * 8) = *reinterpret_cast<const uint4*>(l);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 4)
+// Explicit shared-state-space accesses on 32-bit addresses: keeps the solver on LDS/STS (pointer
+// arithmetic through uintptr_t otherwise degrades to generic LD/ST) and halves address registers.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float a) {
+  asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(a) : "memory");
+}
+
+// Packed fp32x2 arithmetic (sm_100 FFMA2): two row elements per 64-bit register, one instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;\n" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;\n" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {   // a * b + c, both halves
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void lds128x2(uint32_t addr, f32x2& p0, f32x2& p1) {
+  asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];\n" : "=l"(p0), "=l"(p1) : "r"(addr));
+}
+__device__ __forceinline__ f32x2 lds64x2(uint32_t addr) {
+  f32x2 p;
+  asm volatile("ld.shared.b64 %0, [%1];\n" : "=l"(p) : "r"(addr));
+  return p;
+}
+__device__ __forceinline__ void sts128x2(uint32_t addr, f32x2 p0, f32x2 p1) {
+  asm volatile("st.shared.v2.b64 [%0], {%1,%2};\n" ::"r"(addr), "l"(p0), "l"(p1) : "memory");
+}
+
+// Predicated (branch-free) shared stores: the pivot owner publishes without diverging its warp.
+__device__ __forceinline__ void sts128x2_if(bool pred, uint32_t addr, f32x2 p0, f32x2 p1) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.b64 [%0], {%1,%2};\n\t}\n"
+               ::"r"(addr), "l"(p0), "l"(p1), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ void sts32_if(bool pred, uint32_t addr, float a) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}\n"
+               ::"r"(addr), "f"(a), "r"((uint32_t)pred) : "memory");
+}
+
+// Named barriers: 1 = the two solver warps, 2 = the two producer warps (0 is __syncthreads).
+__device__ __forceinline__ void bar_sync_64(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
+
+// Register-resident solve of one 64x64 SPD system by the two solver warps (thread m owns row m
+// of the symmetric matrix, a[0..63], and its right-hand side element a[64]).
+// Square-root-free Cholesky (A = L D L^T, the same elimination dppsv performs up to the scaling
+// of the columns): at step j the owner of row j publishes its raw row and 1/d_j
+// (P[j][c] = a_j[c] for c > j, P[j][j] = 1/a_j[j]); every later row m does
+//   w = a_m[j] / d_j ;  a_m[c] -= w * a_j[c]   for c in (j, 64]
+// over its full remaining width (both triangles + rhs), so row j is complete when its turn
+// comes and one broadcast per step is all the communication.  Steps 0..31 involve both warps
+// (bar.sync among 64 threads); steps 32..63 live in warp 1 alone (__syncwarp).
+// After the elimination a_m[64] = (L^-1 b)_m and the owner's registers a_c[j], j > c, still hold
+// its raw pivot row, so the back substitution  x_c = (y_c - sum_{j>c} a_c[j] x_j) / d_c  runs out
+// of each thread's own registers; only x_j travels (shuffles inside a warp, one shared-memory
+// hand-over from warp 1 to warp 0).  Returns x_m.
+template <int LDP>
+__device__ __forceinline__ float ldlt64_rows(f32x2 (&ap)[32], float rhs, uint32_t P /* shared address */, int m,
+                                             long long* pfs = nullptr) {
+  // ap[i] = (a[2i], a[2i+1]) of this thread's matrix row; rhs = its right-hand side element (a[64])
+  const int lane = m & 31;
+  float inv_d = 0.f;
+#ifdef HALS_TC_PROFILE
+  long long ts = clock64();
+#define HALS_PFS(i) do { const long long n__ = clock64(); pfs[i] += n__ - ts; ts = n__; } while (0)
+#else
+#define HALS_PFS(i) do { } while (0)
+#endif
+  // The 64 elimination steps are NOT unrolled end to end (that is ~70 KB of straight-line code per
+  // row and the solver then starves on instruction fetch); instead the row lives in a rotating
+  // register window: 8 pivots per loop iteration are handled at fixed register positions 0..7, then
+  // the window is rotated by 8 columns.  Register r holds absolute column (r + 8b) mod 64 in
+  // iteration b; after 8 iterations every row is back in absolute alignment.  The pivot owner
+  // publishes its whole window, so readers and owner agree on the rotation by construction.
+  // Finished rows (m <= j) use a zero multiplier: their frozen pivot rows are never modified.
+#define HALS_LDLT_STEP(NPAIRS, SYNC)                                                                  \
+  {                                                                                                   \
+    const int j = 8 * b + jj;                                                                         \
+    const uint32_t Pj = P + j * LDP * 4;                                                              \
+    const float aj = (jj & 1) ? hi2(ap[jj / 2]) : lo2(ap[jj / 2]);                                    \
+    const bool own = (m == j);                                                                        \
+    const float inv = __fdividef(1.0f, aj);                                                           \
+    if (own) inv_d = inv;                                                                             \
+    _Pragma("unroll") for (int c4 = (jj / 4) * 4; c4 < 2 * (NPAIRS); c4 += 4) {                       \
+      f32x2 p0 = ap[c4 / 2], p1 = ap[c4 / 2 + 1];                                                     \
+      if (jj >= c4 && jj < c4 + 4) {                                                                  \
+        if (jj - c4 == 0) p0 = pack2(inv, hi2(p0));                                                   \
+        if (jj - c4 == 1) p0 = pack2(lo2(p0), inv);                                                   \
+        if (jj - c4 == 2) p1 = pack2(inv, hi2(p1));                                                   \
+        if (jj - c4 == 3) p1 = pack2(lo2(p1), inv);                                                   \
+      }                                                                                               \
+      sts128x2_if(own, Pj + c4 * 4, p0, p1);                                                          \
+    }                                                                                                 \
+    sts32_if(own, Pj + 64 * 4, rhs);                                                                  \
+    SYNC;                                                                                             \
+    const float nw = (m > j) ? -aj * lds32(Pj + jj * 4) : 0.f;                                        \
+    const f32x2 nw2 = pack2(nw, nw);                                                                  \
+    _Pragma("unroll") for (int i = ((jj + 1) / 4) * 2; i < (NPAIRS); i += 2) {                        \
+      f32x2 q0, q1;                                                                                   \
+      lds128x2(Pj + i * 8, q0, q1);                                                                   \
+      ap[i] = ffma2(nw2, q0, ap[i]);                                                                  \
+      ap[i + 1] = ffma2(nw2, q1, ap[i + 1]);                                                          \
+    }                                                                                                 \
+    rhs = fmaf(nw, lds32(Pj + 64 * 4), rhs);                                                          \
+  }
+#define HALS_LDLT_ROTATE()                                                                            \
+  {                                                                                                   \
+    const f32x2 t0 = ap[0], t1 = ap[1], t2 = ap[2], t3 = ap[3];                                       \
+    _Pragma("unroll") for (int i = 0; i < 28; ++i) ap[i] = ap[i + 4];                                 \
+    ap[28] = t0; ap[29] = t1; ap[30] = t2; ap[31] = t3;                                               \
+  }
+#pragma unroll 1
+  for (int b = 0; b < 4; ++b) {                          // pivots 0..31: both warps, full window
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) HALS_LDLT_STEP(32, bar_sync_64(1))
+    HALS_LDLT_ROTATE()
+  }
+  HALS_PFS(0);
+  if (m >= 32) {
+#pragma unroll 1
+    for (int b = 4; b < 8; ++b) {                        // pivots 32..63: warp 1 alone; live columns fit 16 pairs
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) HALS_LDLT_STEP(16, __syncwarp())
+      HALS_LDLT_ROTATE()
+    }
+  } else {                                               // warp 0: finish the rotation (4 x 8 columns)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const f32x2 tmp = ap[i]; ap[i] = ap[i + 16]; ap[i + 16] = tmp; }
+  }
+  HALS_PFS(1);
+  // ---- back substitution ------------------------------------------------------------------------
+  float acc = rhs;
+  float x = 0.f;
+  const uint32_t X = P + 64 * LDP * 4;                   // x_32..x_63 handed from warp 1 to warp 0
+  if (m >= 32) {
+#pragma unroll
+    for (int j = 63; j >= 32; --j) {
+      const float xj = __shfl_sync(0xffffffffu, acc * inv_d, j - 32);   // lane j-32 owns x_j
+      if (m == j) x = xj;
+      const float aj = (j & 1) ? hi2(ap[j / 2]) : lo2(ap[j / 2]);
+      if (m < j) acc = fmaf(-aj, xj, acc);
+    }
+    sts32(X + lane * 4, x);
+  }
+  HALS_PFS(2);
+  bar_sync_64(1);
+  HALS_PFS(3);
+  if (m < 32) {
+#pragma unroll
+    for (int j4 = 60; j4 >= 32; j4 -= 4) {
+      const float4 q = lds128(X + (j4 - 32) * 4);
+      acc = fmaf(-hi2(ap[j4 / 2 + 1]), q.w, acc);
+      acc = fmaf(-lo2(ap[j4 / 2 + 1]), q.z, acc);
+      acc = fmaf(-hi2(ap[j4 / 2]), q.y, acc);
+      acc = fmaf(-lo2(ap[j4 / 2]), q.x, acc);
+    }
+#pragma unroll
+    for (int j = 31; j >= 0; --j) {
+      const float xj = __shfl_sync(0xffffffffu, acc * inv_d, j);
+      if (m == j) x = xj;
+      const float aj = (j & 1) ? hi2(ap[j / 2]) : lo2(ap[j / 2]);
+      if (m < j) acc = fmaf(-aj, xj, acc);
+    }
+  }
+  HALS_PFS(4);
+  return x;
+}
+
+#ifndef HALS_TC_CTAS_PER_SM
+#define HALS_TC_CTAS_PER_SM 4
+#endif
+__global__ void __launch_bounds__(kTcThreads, HALS_TC_CTAS_PER_SM)
 als_tc64_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                 const __nv_bfloat16* __restrict__ src_hl, float* __restrict__ dst, float reg,
                 const int32_t* __restrict__ item_row, const int64_t* __restrict__ item_begin,
                 const int32_t* __restrict__ item_len, const int32_t* __restrict__ item_slot,
-                int64_t n_items, float* __restrict__ workspace) {
-  constexpr int K = kTcK, KC = kTcKC, LD = kTcLD;
+                int64_t n_items, float* __restrict__ workspace, int n_sm) {
+  constexpr int K = kTcK, KC = kTcKC, LD = kTcLD, LDP = kTcLDP;
   extern __shared__ uint8_t smem_dyn[];
   __shared__ uint64_t mbar_free[kTcStages];
   __shared__ uint64_t mbar_acc;
   __shared__ uint32_t tmem_slot;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  float* S1 = reinterpret_cast<float*>(base + kTcStages * kTcStageBytes);  // normal matrix + rhs row
-  float* S2 = reinterpret_cast<float*>(base);                              // aliases the stage ring (epilogue only)
+  float* P = reinterpret_cast<float*>(base + kTcStages * kTcStageBytes);   // published pivot rows (solver warps only)
+  float* S2 = reinterpret_cast<float*>(base);                              // l h^T block; aliases the stage ring
   float* S2b = S2 + K * LD;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int t_sub = tid >> 4, piece = tid & 15;      // gather role: rating row within 8, 16-byte piece of the 256 B row
+  // Roles alternate with the CTA parity so that the solver warps of the co-resident CTAs spread
+  // over all four SM sub-partitions (warp w issues on sub-partition w % 4): even CTAs solve on
+  // warps 0,1 and produce on warps 2,3; odd CTAs the other way round (with the h / l blocks of the
+  // stage swapped, so the solver pair always drains the h h^T rows from its own TMEM lanes).
+  const bool swap = ((blockIdx.x / n_sm) & 1) != 0;   // CTAs b and b + n_sm share an SM
+  const bool producer = swap ? (tid < 64) : (tid >= 64);
+  const int ptid = swap ? tid : tid - 64;            // producer thread index 0..63
+  const int stid = swap ? tid - 64 : tid;            // solver thread index = matrix row
+  const int off_h = swap ? kTcBlk : 0, off_l = swap ? 0 : kTcBlk;
+  const int t_sub = ptid >> 4, piece = ptid & 15;    // gather role: rating row within 4, 16-byte piece of the 256 B row
   if (warp == 0) umma::tmem_alloc(&tmem_slot, kTcTmemCols);
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) umma::mbar_init(&mbar_free[s], 1);
@@ -91,6 +289,14 @@ als_tc64_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ va
   const uint32_t sbase = umma::smem_u32(base);
   constexpr uint32_t idesc = umma::make_instr_desc(umma::kFmtBF16, true, true, 128, kTcN);
 
+#ifdef HALS_TC_PROFILE
+  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pfs[5] = {0, 0, 0, 0, 0};
+  long long tp = clock64();
+#define HALS_PF(i) do { const long long n__ = clock64(); pf[i] += n__ - tp; tp = n__; } while (0)
+#else
+#define HALS_PF(i) do { } while (0)
+#endif
   uint32_t g = 0;         // chunks produced so far by this CTA (stage = g % stages)
   uint32_t acc_phase = 0;
 
@@ -101,106 +307,133 @@ als_tc64_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ va
     const int slot = item_slot[item];
     const int nc = (len + KC - 1) / KC;
 
-    auto produce = [&](int c) {
-      const uint32_t gi = g + c, s = gi % kTcStages, u = gi / kTcStages;
-      if (u > 0) umma::mbar_wait(&mbar_free[s], (u - 1) & 1);
-      uint8_t* st = base + s * kTcStageBytes;
-      // the 16 threads sharing t read one contiguous 256-byte h|l row
-      const int blk_off = (piece < 8 ? 0 : kTcBlk);
-      const int chunk = piece & 7;
-#pragma unroll
-      for (int i = 0; i < KC / 8; ++i) {
-        const int t = t_sub + 8 * i;
-        const int q = c * KC + t;
-        const bool ok = q < len;
-        const int ci = ok ? __ldg(colidx + begin + q) : 0;
-        cp_async16(st + blk_off + t * kTcRowBytes + ((chunk ^ (t & 7)) << 4),
-                   reinterpret_cast<const uint8_t*>(src_hl) + (size_t)ci * (4 * K) + piece * 16, ok);
-      }
-      if (warp == 0) {      // rating column(s) of the B operand: element 0 = bf16(r), element 1 = bf16(r - bf16(r))
+    if (producer) {
+      // lane t of each producer warp holds (column index, rating) of rating t of a chunk, fetched one
+      // chunk ahead of its use so the dependent gather never waits on the index load
+      auto fetch_idx = [&](int c, int& ci, float& rv) {
         const int q = c * KC + lane;
-        const float r = q < len ? __ldg(vals + begin + q) : 0.f;
-        const __nv_bfloat16 rh = __float2bfloat16_rn(r);
-        const __nv_bfloat16 rl = __float2bfloat16_rn(r - __bfloat162float(rh));
-        const uint32_t packed = (uint32_t)__bfloat16_as_ushort(rh) | ((uint32_t)__bfloat16_as_ushort(rl) << 16);
-        uint4 v = make_uint4(packed, 0u, 0u, 0u);
-        // chunks 0 and 1 of the row (N columns 64..79), swizzled
-        *reinterpret_cast<uint4*>(st + 2 * kTcBlk + lane * kTcRowBytes + ((0 ^ (lane & 7)) << 4)) = v;
-        *reinterpret_cast<uint4*>(st + 2 * kTcBlk + lane * kTcRowBytes + ((1 ^ (lane & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-      }
-      cp_async_commit();
-    };
-
-    for (int c = 0; c < kTcAhead; ++c) {
-      if (c < nc) produce(c); else cp_async_commit();
-    }
-    for (int c = 0; c < nc; ++c) {
-      if (c + kTcAhead < nc) produce(c + kTcAhead); else cp_async_commit();
-      cp_async_wait<kTcAhead>();
-      umma::fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-        umma::fence_after_sync();
-        const uint32_t s = (g + c) % kTcStages;
-        const uint32_t sa = sbase + s * kTcStageBytes;
+        const bool ok = q < len;
+        ci = ok ? __ldg(colidx + begin + q) : -1;
+        rv = (ok && ptid < 32) ? __ldg(vals + begin + q) : 0.f;
+      };
+      int ci_cur, ci_nxt = -1;
+      float rv_cur, rv_nxt = 0.f;
+      fetch_idx(0, ci_cur, rv_cur);
+      if (nc > 1) fetch_idx(1, ci_nxt, rv_nxt);
+      auto produce = [&](int c) {
+        const uint32_t gi = g + c, s = gi % kTcStages, u = gi / kTcStages;
+        if (u > 0) umma::mbar_wait(&mbar_free[s], (u - 1) & 1);
+        uint8_t* st = base + s * kTcStageBytes;
+        // the 16 threads sharing t read one contiguous 256-byte h|l row
+        const int blk_off = (piece < 8 ? off_h : off_l);
+        const int chunk = piece & 7;
 #pragma unroll
-        for (int ks = 0; ks < KC / 16; ++ks) {
-          const uint64_t ad = umma::make_smem_desc(sa + ks * 2048, kTcBlk, 1024, umma::kSwizzle128B);
-          const uint64_t bd = umma::make_smem_desc(sa + ks * 2048, 2 * kTcBlk, 1024, umma::kSwizzle128B);
-          umma::mma_bf16(tmem, ad, bd, idesc, (c | ks) != 0);
+        for (int i = 0; i < KC / 4; ++i) {
+          const int t = t_sub + 4 * i;
+          const int ci = __shfl_sync(0xffffffffu, ci_cur, t);
+          cp_async16(st + blk_off + t * kTcRowBytes + ((chunk ^ (t & 7)) << 4),
+                     reinterpret_cast<const uint8_t*>(src_hl) + (size_t)(ci < 0 ? 0 : ci) * (4 * K) + piece * 16, ci >= 0);
         }
-        umma::commit(&mbar_free[s]);
-        if (c == nc - 1) umma::commit(&mbar_acc);
+        if (ptid < 32) {    // rating columns of the B operand: element 0 = bf16(r), element 1 = bf16(r - bf16(r))
+          const __nv_bfloat16 rh = __float2bfloat16_rn(rv_cur);
+          const __nv_bfloat16 rl = __float2bfloat16_rn(rv_cur - __bfloat162float(rh));
+          const uint32_t packed = (uint32_t)__bfloat16_as_ushort(rh) | ((uint32_t)__bfloat16_as_ushort(rl) << 16);
+          // chunks 0 and 1 of the row (N columns 64..79), swizzled
+          *reinterpret_cast<uint4*>(st + 2 * kTcBlk + lane * kTcRowBytes + ((0 ^ (lane & 7)) << 4)) = make_uint4(packed, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(st + 2 * kTcBlk + lane * kTcRowBytes + ((1 ^ (lane & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        cp_async_commit();
+        ci_cur = ci_nxt; rv_cur = rv_nxt;
+        if (c + 2 < nc) fetch_idx(c + 2, ci_nxt, rv_nxt);
+      };
+      for (int c = 0; c < kTcAhead; ++c) {
+        if (c < nc) produce(c); else cp_async_commit();
+      }
+      for (int c = 0; c < nc; ++c) {
+        if (c + kTcAhead < nc) produce(c + kTcAhead); else cp_async_commit();
+        cp_async_wait<kTcAhead>();
+        umma::fence_proxy_async();
+        bar_sync_64(2);
+        if (ptid == 0) {
+          umma::fence_after_sync();
+          const uint32_t s = (g + c) % kTcStages;
+          const uint32_t sa = sbase + s * kTcStageBytes;
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint64_t ad = umma::make_smem_desc(sa + ks * 2048, kTcBlk, 1024, umma::kSwizzle128B);
+            const uint64_t bd = umma::make_smem_desc(sa + off_h + ks * 2048, 2 * kTcBlk - off_h, 1024, umma::kSwizzle128B);
+            umma::mma_bf16(tmem, ad, bd, idesc, (c | ks) != 0);
+          }
+          umma::commit(&mbar_free[s]);
+          if (c == nc - 1) umma::commit(&mbar_acc);
+        }
       }
     }
     g += nc;
+    HALS_PF(0);   // producer: gather+mma issue / solver: ~0
 
-    // ---- epilogue: TMEM -> registers -> combine through shared memory ------------------------------
+    // ---- drain: TMEM -> registers (all four warps: a warp reads only its own 32 TMEM lanes) -----------
     umma::mbar_wait(&mbar_acc, acc_phase);
     acc_phase ^= 1;
+    HALS_PF(1);   // wait for the accumulator
     umma::fence_after_sync();
-    {
-      const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16);
-      float v0[32], v1[32], e[16];
-      umma::tmem_ld32(ta, v0);
-      umma::tmem_ld32(ta + 32, v1);
-      umma::tmem_ld16(ta + 64, e);
-      umma::fence_before_sync();
-      if (tid >= 64) {  // l h^T rows
-        float* r2 = S2 + (tid - 64) * LD;
+    const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16);
+    float a[65], e[16];
+    umma::tmem_ld32(ta, a);
+    umma::tmem_ld32(ta + 32, a + 32);
+    umma::tmem_ld16(ta + 64, e);
+    umma::fence_before_sync();
+    if (producer) {     // l h^T rows go through shared memory
+      float* r2 = S2 + ptid * LD;
 #pragma unroll
-        for (int n = 0; n < 32; ++n) { r2[n] = v0[n]; r2[32 + n] = v1[n]; }
-        S2b[tid - 64] = e[0];
-      }
-      __syncthreads();
-      if (tid < 64) {
-        const int m = tid;
-        float* r1 = S1 + m * LD;
+      for (int n = 0; n < 64; ++n) r2[n] = a[n];
+      S2b[ptid] = e[0];
+    }
+    HALS_PF(2);   // drain
+    __syncthreads();
+    HALS_PF(3);   // wait at sync 1
+    if (!producer) {
+      const int m = stid;
+      const float lam = slot >= 0 ? 0.f : reg * (float)len;
 #pragma unroll
-        for (int n = 0; n < 32; ++n) {
-          r1[n] = v0[n] + S2[m * LD + n] + S2[n * LD + m];
-          r1[32 + n] = v1[n] + S2[m * LD + 32 + n] + S2[(32 + n) * LD + m];
-        }
-        S1[K * LD + m] = e[0] + e[1] + S2b[m];
+      for (int n = 0; n < 64; ++n) a[n] += S2[m * LD + n] + S2[n * LD + m] + (n == m ? lam : 0.f);
+      a[64] = e[0] + e[1] + S2b[m];
+    }
+    HALS_PF(4);   // combine
+    __syncthreads();    // S2 (stage ring) is free again: the producers may start the next item
+    HALS_PF(5);   // wait at sync 2
+    if (!producer) {
+      const int m = stid;
+      if (slot >= 0) {
+        // slice of a long row: park (A, b, n) in the slot (same layout as the SIMT path)
+        float* W = workspace + (size_t)slot * ((size_t)K * K + K + 4);
+#pragma unroll
+        for (int n = 0; n < 64; n += 4)
+          *reinterpret_cast<float4*>(W + m * K + n) = make_float4(a[n], a[n + 1], a[n + 2], a[n + 3]);
+        W[K * K + m] = a[64];
+        if (m == 0) W[K * K + K] = (float)len;
+      } else {
+        f32x2 ap[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ap[i] = pack2(a[2 * i], a[2 * i + 1]);
+#ifdef HALS_TC_PROFILE
+        const float x = ldlt64_rows<LDP>(ap, a[64], umma::smem_u32(P), m, pfs);
+#else
+        const float x = ldlt64_rows<LDP>(ap, a[64], umma::smem_u32(P), m);
+#endif
+        dst[(int64_t)row * K + m] = x;
+        bar_sync_64(1);   // P is reused by the next item
       }
-      if (tid == 0) S1[K * LD + K] = (float)len;
-      __syncthreads();
     }
-    if (slot >= 0) {
-      // slice of a long row: park (A, b, n) in the slot (same layout as the SIMT path)
-      float* W = workspace + (size_t)slot * ((size_t)K * K + K + 4);
-      for (int e2 = tid; e2 < K * K; e2 += kTcThreads) W[e2] = S1[(e2 >> 6) * LD + (e2 & 63)];
-      if (tid <= K) W[K * K + tid] = S1[K * LD + tid];
-      __syncthreads();
-    } else {
-      if (tid < K) S1[tid * LD + tid] += reg * (float)len;
-      __syncthreads();
-      cholesky_solve_smem<K>(S1, K);
-      if (tid < K) dst[(int64_t)row * K + tid] = S1[K * LD + tid];
-      __syncthreads();
-    }
+    HALS_PF(6);   // solve
   }
 
+#ifdef HALS_TC_PROFILE
+  if ((tid % 32 == 0) && blockIdx.x < 1) printf("   tid %d solver phases: elim0-31 %lld elim32-63 %lld back1 %lld bar %lld back0 %lld\n", tid, pfs[0], pfs[1], pfs[2], pfs[3], pfs[4]);
+  if ((tid == 0 || tid == 64) && blockIdx.x < 2)
+    printf("cta %d tid %d items %d: gather %lld accwait %lld drain %lld sync1 %lld combine %lld sync2 %lld solve %lld\n",
+           blockIdx.x, tid, (int)((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x), pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6]);
+#endif
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, kTcTmemCols);
@@ -214,11 +447,12 @@ int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* sr
   HALS_LAUNCH_CHECK();
   const size_t smem = (size_t)kTcStages * kTcStageBytes + kTcS1Floats * sizeof(float) + 1024;
   HALS_CUDA(cudaFuncSetAttribute(als_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int64_t grid = 4 * (int64_t)sm_count();
+  static const int grid_mult = [] { const char* e = getenv("HALS_TC_GRID_MULT"); return e ? atoi(e) : HALS_TC_CTAS_PER_SM; }();
+  int64_t grid = grid_mult * (int64_t)sm_count();
   if (grid > plan->n_items) grid = plan->n_items;
   als_tc64_kernel<<<(unsigned)grid, kTcThreads, smem, st>>>(colidx, vals, hl, dst, reg, plan->item_row,
                                                              plan->item_begin, plan->item_len, plan->item_slot,
-                                                             plan->n_items, slots);
+                                                             plan->n_items, slots, sm_count());
   HALS_LAUNCH_CHECK();
   return als_launch_reduce_solve(slots, dst, kTcK, reg, nullptr, plan, st);
 }

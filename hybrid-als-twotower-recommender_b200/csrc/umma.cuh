@@ -69,7 +69,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // 32 lanes x 16 consecutive columns: thread i of the warp receives row (lane base + i).
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* __restrict__ v) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -80,7 +80,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* __restrict__ v) {
   uint32_t r[32];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
