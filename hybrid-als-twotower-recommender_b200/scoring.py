@@ -34,6 +34,46 @@ def merge_lists(part_idx: torch.Tensor, part_score: torch.Tensor):
     return out_idx, out_score
 
 
+def exchange_topk(idx, sc, rank: int, world: int, merge_fn):
+    """Cross-shard merge of per-shard top-k lists ([U,k] on every rank, global item numbering).
+
+    All-to-all: rank j receives, from every rank, the lists of ITS equal chunk of the users
+    ([world, ceil(U/world), k]) and merges them with `merge_fn` -- each rank ends up owning the final
+    top-k of U/world users (0.8 GB received per GPU at config 5 instead of 6.4 GB for an all-gather).
+    Single-rank: returns the inputs unchanged."""
+    dist = _dist()
+    if dist is None or world == 1:
+        return idx, sc
+    n, k = idx.shape
+    per = (n + world - 1) // world
+    pad = per * world - n
+    if pad:
+        idx = torch.cat([idx, torch.full((pad, k), -1, dtype=idx.dtype, device=idx.device)])
+        sc = torch.cat([sc, torch.full((pad, k), float("-inf"), dtype=sc.dtype, device=sc.device)])
+    ridx, rsc = torch.empty_like(idx), torch.empty_like(sc)
+    dist.all_to_all_single(ridx, idx.contiguous())     # chunk j of my lists -> rank j
+    dist.all_to_all_single(rsc, sc.contiguous())
+    return merge_fn(ridx.view(world, per, k), rsc.view(world, per, k))
+
+
+def reduce_extrema(ex, world: int):
+    """(min_a, max_a, min_t, max_t) per user -> global over all item shards: one MAX all-reduce
+    on the sign-flipped minima."""
+    dist = _dist()
+    if dist is None or world == 1:
+        return ex
+    sign = torch.tensor([-1.0, 1.0, -1.0, 1.0], device=ex.device, dtype=ex.dtype)
+    ex = ex * sign
+    dist.all_reduce(ex, op=dist.ReduceOp.MAX)
+    return ex * sign
+
+
+def shard_items(n_items: int, rank: int, world: int):
+    """Contiguous equal item shards (item-sharded scoring): [begin, end) of this rank."""
+    per = (n_items + world - 1) // world
+    return min(n_items, rank * per), min(n_items, (rank + 1) * per)
+
+
 class HybridScorer:
     """Holds the four operand matrices of one item shard in HBM (fp32, row-major)."""
 
@@ -63,12 +103,7 @@ class HybridScorer:
         ex = torch.empty((u1 - u0, 4), dtype=torch.float32, device=self.device)
         nat.check(L.hals_score_extrema(*self._ops(u0, u1), u1 - u0, self.n_items, nat.ptr(ex),
                                        nat.current_stream()), "hals_score_extrema")
-        dist = _dist()
-        if dist is not None and self.world > 1:
-            sign = torch.tensor([-1.0, 1.0, -1.0, 1.0], device=self.device)
-            ex *= sign                                  # min -> max of the negation: one MAX all-reduce
-            dist.all_reduce(ex, op=dist.ReduceOp.MAX)
-            ex *= sign
+        ex = reduce_extrema(ex, self.world)
         return ex
 
     def topk_local(self, extrema, k, w_als, w_tt, u0=0, u1=None):
@@ -94,19 +129,7 @@ class HybridScorer:
         u1 = self.n_users if u1 is None else u1
         ex = self.extrema(u0, u1)
         idx, sc = self.topk_local(ex, k, w_als, w_tt, u0, u1)
-        dist = _dist()
-        if dist is None or self.world == 1:
-            return idx, sc
-        n = u1 - u0
-        per = (n + self.world - 1) // self.world
-        pad = per * self.world - n
-        if pad:
-            idx = torch.cat([idx, torch.full((pad, k), -1, dtype=idx.dtype, device=idx.device)])
-            sc = torch.cat([sc, torch.full((pad, k), float("-inf"), dtype=sc.dtype, device=sc.device)])
-        ridx, rsc = torch.empty_like(idx), torch.empty_like(sc)
-        dist.all_to_all_single(ridx, idx)     # chunk j of my lists -> rank j
-        dist.all_to_all_single(rsc, sc)
-        return merge_lists(ridx.view(self.world, per, k), rsc.view(self.world, per, k))
+        return exchange_topk(idx, sc, self.rank, self.world, merge_lists)
 
     def user_slice(self, u0, u1):
         n = u1 - u0
