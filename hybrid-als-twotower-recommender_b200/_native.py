@@ -61,8 +61,9 @@ SIGNATURES = {
     "hals_tower_user": (ctypes.c_int, [ctypes.POINTER(TowerWeights), c_vp, c_i64, c_vp, c_i64, c_vp]),
     "hals_tower_item": (ctypes.c_int, [ctypes.POINTER(TowerWeights), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "hals_score_extrema": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.c_int, c_vp, c_i64, c_vp, c_i64,
-                                          ctypes.c_int, c_i64, c_i64, c_vp, c_vp]),
+                                          ctypes.c_int, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "hals_score_workspace_bytes": (c_sz, [c_i64, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "hals_score_flag_counter_offset": (c_i64, [c_i64, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "hals_score_blend_topk": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.c_int, c_vp, c_i64, c_vp, c_i64,
                                              ctypes.c_int, c_i64, c_i64, c_vp, c_f32, c_f32, ctypes.c_int, c_i32,
                                              c_vp, c_vp, c_vp, c_sz, c_vp]),

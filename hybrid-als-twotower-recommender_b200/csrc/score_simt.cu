@@ -12,6 +12,7 @@
 // The tensor-core path (score_tc.cu) uses this kernel's epilogue machinery and is checked
 // against it; this path is also the exact fallback for shapes the TC path does not take.
 #include "common.cuh"
+#include "score_common.cuh"
 #include "topk.cuh"
 
 namespace hals {
@@ -28,6 +29,13 @@ struct ScoreArgs {
   int ka, kt;
   int64_t n_users, n_items;
   int64_t items_per_split;
+  // optional indirection (exact re-run of flagged users after the tensor-core path): the kernel then
+  // walks user_list[0 .. *user_count) instead of 0 .. n_users, looping over tiles persistently
+  const int32_t* user_list;
+  const int32_t* user_count;
+  // list mode: positions [list_begin, min(*user_count, list_end)) are handled by this launch; candidate /
+  // partial-list rows are addressed by (split, position - list_begin) with `row_stride` rows per split
+  int64_t list_begin, list_end, row_stride;
 };
 
 __device__ __forceinline__ void atomic_min_f32(float* addr, float v) {
@@ -89,35 +97,42 @@ score_simt_kernel(ScoreArgs A, float* __restrict__ extrema_out, const float* __r
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int lane = tid & 31, warp = tid >> 5;
-  const int64_t u0 = (int64_t)blockIdx.x * kScUsers;
   const int split = blockIdx.y;
+  const int64_t n_rows = A.user_list ? min((int64_t)*A.user_count, A.list_end) : A.n_users;
+  const int64_t row_base = A.user_list ? A.list_begin : 0;
+  const int64_t row_stride = A.user_list ? A.row_stride : A.n_users;
+  const bool by_pos = A.user_list != nullptr && gridDim.y > 1;   // partial lists addressed by list position
+  for (int64_t u0 = row_base + (int64_t)blockIdx.x * kScUsers; u0 < n_rows; u0 += (int64_t)gridDim.x * kScUsers) {
+  __syncthreads();
+  // row r of this tile is user uid(r); rows beyond n_rows are padding
+  auto uid = [&](int r) -> int64_t { return A.user_list ? (int64_t)A.user_list[min(u0 + r, n_rows - 1)] : u0 + r; };
   const int64_t i_begin = (int64_t)split * A.items_per_split;
   const int64_t i_end = min(A.n_items, i_begin + A.items_per_split);
 
   // stage the user tile (both models side by side), zero rows beyond n_users
   for (int e = tid; e < kScUsers * K; e += kScThreads) {
     const int r = e / K, f = e - r * K;
-    const int64_t u = u0 + r;
+    const int64_t u = uid(r);
     float v = 0.f;
-    if (u < A.n_users) v = f < A.ka ? A.Ua[u * A.ua_stride + f] : A.Ut[u * A.ut_stride + (f - A.ka)];
+    if (u0 + r < n_rows) v = f < A.ka ? A.Ua[u * A.ua_stride + f] : A.Ut[u * A.ut_stride + (f - A.ka)];
     Us[r * LD + f] = v;
   }
   if (tid < kScUsers) {
     cnt[tid] = 0;
     thr[tid] = kTopkEmpty;
-    const int64_t u = u0 + tid;
+    const int64_t u = uid(tid);
     float4 ex;
     if (EXTREMA) {
       const float inf = __int_as_float(0x7f800000);
       ex = make_float4(inf, -inf, inf, -inf);
     } else {
-      ex = (u < A.n_users) ? reinterpret_cast<const float4*>(extrema_in)[u] : make_float4(0, 1, 0, 1);
+      ex = (u0 + tid < n_rows) ? reinterpret_cast<const float4*>(extrema_in)[u] : make_float4(0, 1, 0, 1);
       const BlendCoef c = blend_coef(ex);
       ex = make_float4(c.min_a, c.sc_a, c.min_t, c.sc_t);
     }
     reinterpret_cast<float4*>(rowstat)[tid] = ex;
   }
-  uint64_t* mycand = EXTREMA ? nullptr : cand + ((size_t)split * A.n_users + u0) * CAP;
+  uint64_t* mycand = EXTREMA ? nullptr : cand + ((size_t)split * row_stride + (u0 - row_base)) * CAP;
 
   for (int64_t it0 = i_begin; it0 < i_end; it0 += kScItems) {
     __syncthreads();
@@ -192,7 +207,7 @@ score_simt_kernel(ScoreArgs A, float* __restrict__ extrema_out, const float* __r
       // warp w filters rows w*8 .. w*8+7; it is the only writer of those rows' buffers
       for (int rr = 0; rr < 8; ++rr) {
         const int r = warp * 8 + rr;
-        if (u0 + r >= A.n_users) break;
+        if (u0 + r >= n_rows) break;
         uint64_t* buf = mycand + (size_t)r * CAP;
         int c = cnt[r];
         uint64_t t = thr[r];
@@ -218,9 +233,9 @@ score_simt_kernel(ScoreArgs A, float* __restrict__ extrema_out, const float* __r
 
   __syncthreads();
   if (EXTREMA) {
-    if (tid < kScUsers && u0 + tid < A.n_users && i_end > i_begin) {
+    if (tid < kScUsers && u0 + tid < n_rows && i_end > i_begin) {
       const float* rs = rowstat + tid * 4;
-      float* ex = extrema_out + (u0 + tid) * 4;
+      float* ex = extrema_out + uid(tid) * 4;
       if (gridDim.y == 1) {
         reinterpret_cast<float4*>(ex)[0] = make_float4(rs[0], rs[1], rs[2], rs[3]);
       } else {
@@ -231,13 +246,14 @@ score_simt_kernel(ScoreArgs A, float* __restrict__ extrema_out, const float* __r
   } else {
     for (int rr = 0; rr < 8; ++rr) {
       const int r = warp * 8 + rr;
-      const int64_t u = u0 + r;
-      if (u >= A.n_users) break;
+      if (u0 + r >= n_rows) break;
+      const int64_t u = uid(r);
       uint64_t* buf = mycand + (size_t)r * CAP;
       uint64_t t;
       const int c = topk_compact<CAP>(buf, cnt[r], topk, lane, &t);
-      int32_t* oi = out_idx + ((size_t)split * A.n_users + u) * topk;
-      float* os = out_score + ((size_t)split * A.n_users + u) * topk;
+      const size_t orow = by_pos ? (size_t)split * row_stride + (size_t)(u0 - row_base + r) : (size_t)split * A.n_users + u;
+      int32_t* oi = out_idx + orow * topk;
+      float* os = out_score + orow * topk;
       for (int e = lane; e < topk; e += 32) {
         if (e < c) {
           const uint64_t key = buf[e];
@@ -250,6 +266,7 @@ score_simt_kernel(ScoreArgs A, float* __restrict__ extrema_out, const float* __r
       }
     }
   }
+  }  // tile loop
 }
 
 // Merge P partial lists per user: one warp per user streams P*topk keys through the same
@@ -257,10 +274,20 @@ score_simt_kernel(ScoreArgs A, float* __restrict__ extrema_out, const float* __r
 template <int CAP>
 __global__ void topk_merge_kernel(const int32_t* __restrict__ part_idx, const float* __restrict__ part_score,
                                   int n_parts, int64_t n_users, int topk, int32_t* __restrict__ out_idx,
-                                  float* __restrict__ out_score) {
+                                  float* __restrict__ out_score, const int32_t* __restrict__ user_list = nullptr,
+                                  const int32_t* __restrict__ user_count = nullptr, int64_t list_begin = 0,
+                                  int64_t list_end = 0) {
   constexpr int R = CAP / 32;
   const int lane = threadIdx.x & 31;
-  const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // plain mode: row u of the [P][n_users] partial arrays -> out[u].  list mode: partial row = list position
+  // (relative to list_begin, n_users rows per part), destination = user_list[position].
+  int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t dst_row = u;
+  if (user_list != nullptr) {
+    const int64_t n = min((int64_t)*user_count, list_end) - list_begin;
+    if (u >= n) return;
+    dst_row = user_list[list_begin + u];
+  }
   if (u >= n_users) return;
   uint64_t v[R];
 #pragma unroll
@@ -291,8 +318,8 @@ __global__ void topk_merge_kernel(const int32_t* __restrict__ part_idx, const fl
     const int e = r * 32 + lane;
     if (e < topk) {
       const bool ok = v[r] != kTopkEmpty;
-      out_idx[u * topk + e] = ok ? topk_key_index(v[r]) : -1;
-      out_score[u * topk + e] = ok ? topk_key_score(v[r]) : -__int_as_float(0x7f800000);
+      out_idx[dst_row * topk + e] = ok ? topk_key_index(v[r]) : -1;
+      out_score[dst_row * topk + e] = ok ? topk_key_score(v[r]) : -__int_as_float(0x7f800000);
     }
   }
 }
@@ -352,7 +379,7 @@ static int score_splits(int64_t n_users, int64_t n_items) {
 
 using namespace hals;
 
-static int check_score_args(const float* Ua, const float* Ia, int ka, const float* Ut, const float* It, int kt,
+int check_score_args(const float* Ua, const float* Ia, int ka, const float* Ut, const float* It, int kt,
                             int64_t n_users, int64_t n_items) {
   HALS_REQUIRE(ka >= 0 && ka <= 128 && kt >= 0 && kt <= 64 && ka + kt > 0, "ka must be <= 128 and kt <= 64");
   HALS_REQUIRE((ka == 0 || (Ua && Ia)) && (kt == 0 || (Ut && It)), "null operand");
@@ -360,80 +387,131 @@ static int check_score_args(const float* Ua, const float* Ia, int ka, const floa
   return 0;
 }
 
-extern "C" int hals_score_extrema(const float* Ua, int64_t ua_stride, const float* Ia, int64_t ia_stride,
-                                  int ka, const float* Ut, int64_t ut_stride, const float* It,
-                                  int64_t it_stride, int kt, int64_t n_users, int64_t n_items,
-                                  float* extrema, void* stream) {
-  if (int rc = check_score_args(Ua, Ia, ka, Ut, It, kt, n_users, n_items)) return rc;
-  HALS_REQUIRE(extrema, "null extrema");
-  if (n_users == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  extrema_init_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(extrema, n_users);
-  HALS_LAUNCH_CHECK();
-  if (n_items == 0) return 0;
+namespace hals {
+
+size_t score_simt_workspace_bytes(int64_t n_users, int64_t n_items, int topk) {
   const int splits = score_splits(n_users, n_items);
-  ScoreArgs A{Ua, ua_stride, Ia, ia_stride, Ut, ut_stride, It, it_stride, ka, kt, n_users, n_items, 0};
+  const size_t cap = topk_capacity(topk);
+  size_t b = (size_t)splits * n_users * cap * sizeof(uint64_t);             // candidate buffers
+  b += (size_t)splits * n_users * topk * (sizeof(int32_t) + sizeof(float));  // partial lists
+  return b + 256;
+}
+
+// rows / splits of the list-mode (exact re-run) launches
+static int64_t list_rows(int64_t n_users) { return n_users < 2048 ? n_users : 2048; }
+static int list_splits(int64_t n_items) {
+  int64_t t = (n_items + kScItems - 1) / kScItems;
+  if (t > 64) t = 64;
+  return (int)(t < 1 ? 1 : t);
+}
+
+size_t score_simt_list_workspace_bytes(int64_t n_users, int64_t n_items, int topk) {
+  const size_t rows = (size_t)list_rows(n_users) * list_splits(n_items);
+  return rows * topk_capacity(topk) * sizeof(uint64_t) + rows * topk * 8 + 256;
+}
+
+static void fill_split(ScoreArgs& A, int64_t n_items, int splits) {
   const int64_t tiles = (n_items + kScItems - 1) / kScItems;
   A.items_per_split = ((tiles + splits - 1) / splits) * kScItems;
-  const size_t smem = score_smem_bytes(ka + kt);
+  if (A.items_per_split == 0) A.items_per_split = kScItems;
+}
+
+// Exact extrema.  With a user list (device list + device count) only the listed users are recomputed
+// (item-split, combined with order-independent atomic min/max); their rows must have been reset to
+// (+inf,-inf,+inf,-inf) beforehand (score_flag_list_kernel does it) and every other row is left alone.
+int score_extrema_simt(const ScoreOperands& O, int64_t n_users, int64_t n_items, float* extrema,
+                       const int32_t* user_list, const int32_t* user_count, cudaStream_t st) {
+  ScoreArgs A{O.Ua, O.ua_stride, O.Ia, O.ia_stride, O.Ut, O.ut_stride, O.It, O.it_stride, O.ka, O.kt,
+              n_users, n_items, 0, user_list, user_count, 0, n_users, n_users};
+  const bool listed = user_list != nullptr;
+  if (!listed) {
+    extrema_init_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(extrema, n_users);
+    HALS_LAUNCH_CHECK();
+    if (n_items == 0) return 0;
+  }
+  const int splits = listed ? (list_splits(n_items) > 1 ? list_splits(n_items) : 2) : score_splits(n_users, n_items);
+  fill_split(A, n_items, splits);
+  const size_t smem = score_smem_bytes(O.ka + O.kt);
   HALS_CUDA(cudaFuncSetAttribute(score_simt_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((n_users + kScUsers - 1) / kScUsers), (unsigned)splits);
+  int64_t gx = (n_users + kScUsers - 1) / kScUsers;
+  if (listed && gx > 32) gx = 32;                 // persistent over the (device-side) list length
+  dim3 grid((unsigned)gx, (unsigned)splits);
   score_simt_kernel<true, 128><<<grid, kScThreads, smem, st>>>(A, extrema, nullptr, 0.f, 0.f, 0, 0, nullptr,
                                                                  nullptr, nullptr);
   HALS_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" size_t hals_score_workspace_bytes(int64_t n_users, int64_t n_items, int ka, int kt, int topk) {
-  (void)ka; (void)kt;
-  const int splits = score_splits(n_users, n_items);
-  const size_t cap = topk_capacity(topk);
-  size_t b = (size_t)splits * n_users * cap * sizeof(uint64_t);            // candidate buffers
-  b += (size_t)splits * n_users * topk * (sizeof(int32_t) + sizeof(float)); // partial lists
-  return b + 256;
-}
-
-extern "C" int hals_score_blend_topk(const float* Ua, int64_t ua_stride, const float* Ia, int64_t ia_stride,
-                                     int ka, const float* Ut, int64_t ut_stride, const float* It,
-                                     int64_t it_stride, int kt, int64_t n_users, int64_t n_items,
-                                     const float* extrema, float w_als, float w_tt, int topk,
-                                     int32_t item_offset, int32_t* out_idx, float* out_score,
-                                     void* workspace, size_t workspace_bytes, void* stream) {
-  if (int rc = check_score_args(Ua, Ia, ka, Ut, It, kt, n_users, n_items)) return rc;
-  HALS_REQUIRE(extrema && out_idx && out_score && workspace, "null pointer");
-  HALS_REQUIRE(topk >= 1 && topk <= 256, "topk must be in [1,256]");
-  if (workspace_bytes < hals_score_workspace_bytes(n_users, n_items, ka, kt, topk))
-    return fail(HALS_ERR_WORKSPACE, "%s: workspace too small%s", __func__);
-  if (n_users == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int splits = score_splits(n_users, n_items);
-  const int cap = topk_capacity(topk);
-  ScoreArgs A{Ua, ua_stride, Ia, ia_stride, Ut, ut_stride, It, it_stride, ka, kt, n_users, n_items, 0};
-  const int64_t tiles = (n_items + kScItems - 1) / kScItems;
-  A.items_per_split = ((tiles + splits - 1) / splits) * kScItems;
-  if (A.items_per_split == 0) A.items_per_split = kScItems;
-  uint64_t* cand = (uint64_t*)workspace;
-  int32_t* pidx = (int32_t*)(cand + (size_t)splits * n_users * cap);
-  float* pscore = (float*)(pidx + (size_t)splits * n_users * topk);
-  int32_t* oi = splits == 1 ? out_idx : pidx;
-  float* os = splits == 1 ? out_score : pscore;
-  const size_t smem = score_smem_bytes(ka + kt);
-  dim3 grid((unsigned)((n_users + kScUsers - 1) / kScUsers), (unsigned)splits);
-#define HALS_SCORE_LAUNCH(CAPV)                                                                              \
-  do {                                                                                                       \
-    HALS_CUDA(cudaFuncSetAttribute(score_simt_kernel<false, CAPV>,                                           \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-    score_simt_kernel<false, CAPV><<<grid, kScThreads, smem, st>>>(A, nullptr, extrema, w_als, w_tt, topk,   \
-                                                                     item_offset, cand, oi, os);              \
-    HALS_LAUNCH_CHECK();                                                                                     \
-  } while (0)
-  if (cap == 128) HALS_SCORE_LAUNCH(128);
-  else if (cap == 256) HALS_SCORE_LAUNCH(256);
-  else HALS_SCORE_LAUNCH(512);
-#undef HALS_SCORE_LAUNCH
-  if (splits > 1) return hals_topk_merge(pidx, pscore, splits, n_users, topk, out_idx, out_score, stream);
+template <bool EX, int CAPV>
+static int launch_simt_topk(const ScoreArgs& A, dim3 grid, size_t smem, const float* extrema, float w_als, float w_tt,
+                            int topk, int32_t item_offset, uint64_t* cand, int32_t* oi, float* os, cudaStream_t st) {
+  HALS_CUDA(cudaFuncSetAttribute(score_simt_kernel<EX, CAPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  score_simt_kernel<EX, CAPV><<<grid, kScThreads, smem, st>>>(A, nullptr, extrema, w_als, w_tt, topk, item_offset, cand, oi, os);
+  HALS_LAUNCH_CHECK();
   return 0;
 }
+static int launch_simt_topk_cap(int cap, const ScoreArgs& A, dim3 grid, size_t smem, const float* extrema, float w_als,
+                                float w_tt, int topk, int32_t item_offset, uint64_t* cand, int32_t* oi, float* os,
+                                cudaStream_t st) {
+  if (cap == 128) return launch_simt_topk<false, 128>(A, grid, smem, extrema, w_als, w_tt, topk, item_offset, cand, oi, os, st);
+  if (cap == 256) return launch_simt_topk<false, 256>(A, grid, smem, extrema, w_als, w_tt, topk, item_offset, cand, oi, os, st);
+  return launch_simt_topk<false, 512>(A, grid, smem, extrema, w_als, w_tt, topk, item_offset, cand, oi, os, st);
+}
+
+int score_blend_topk_simt(const ScoreOperands& O, int64_t n_users, int64_t n_items, const float* extrema,
+                          float w_als, float w_tt, int topk, int32_t item_offset, int32_t* out_idx,
+                          float* out_score, void* workspace, const int32_t* user_list, const int32_t* user_count,
+                          cudaStream_t st) {
+  const int cap = topk_capacity(topk);
+  const size_t smem = score_smem_bytes(O.ka + O.kt);
+  ScoreArgs A{O.Ua, O.ua_stride, O.Ia, O.ia_stride, O.Ut, O.ut_stride, O.It, O.it_stride, O.ka, O.kt,
+              n_users, n_items, 0, user_list, user_count, 0, n_users, n_users};
+  if (user_list == nullptr) {
+    const int splits = score_splits(n_users, n_items);
+    fill_split(A, n_items, splits);
+    uint64_t* cand = (uint64_t*)workspace;
+    int32_t* pidx = (int32_t*)(cand + (size_t)splits * n_users * cap);
+    float* pscore = (float*)(pidx + (size_t)splits * n_users * topk);
+    dim3 grid((unsigned)((n_users + kScUsers - 1) / kScUsers), (unsigned)splits);
+    if (int rc = launch_simt_topk_cap(cap, A, grid, smem, extrema, w_als, w_tt, topk, item_offset, cand,
+                                      splits == 1 ? out_idx : pidx, splits == 1 ? out_score : pscore, st)) return rc;
+    if (splits > 1) return hals_topk_merge(pidx, pscore, splits, n_users, topk, out_idx, out_score, (void*)st);
+    return 0;
+  }
+  // exact re-run of a device-side user list.  The first list_rows() positions are item-split (fast even for a
+  // handful of users against millions of items) and merged per position; any further positions run unsplit.
+  const int64_t rows = list_rows(n_users);
+  const int splits = list_splits(n_items) > 1 ? list_splits(n_items) : 2;
+  uint64_t* cand = (uint64_t*)workspace;
+  int32_t* pidx = (int32_t*)(cand + (size_t)splits * rows * cap);
+  float* pscore = (float*)(pidx + (size_t)splits * rows * topk);
+  A.list_begin = 0; A.list_end = rows; A.row_stride = rows;
+  fill_split(A, n_items, splits);
+  int64_t gx = (rows + kScUsers - 1) / kScUsers;
+  if (gx > 32) gx = 32;
+  if (int rc = launch_simt_topk_cap(cap, A, dim3((unsigned)gx, (unsigned)splits), smem, extrema, w_als, w_tt, topk,
+                                    item_offset, cand, pidx, pscore, st)) return rc;
+  {
+    const unsigned blocks = (unsigned)((rows + 3) / 4);
+    if (cap == 128) topk_merge_kernel<128><<<blocks, 128, 0, st>>>(pidx, pscore, splits, rows, topk, out_idx, out_score, user_list, user_count, 0, rows);
+    else if (cap == 256) topk_merge_kernel<256><<<blocks, 128, 0, st>>>(pidx, pscore, splits, rows, topk, out_idx, out_score, user_list, user_count, 0, rows);
+    else topk_merge_kernel<512><<<blocks, 128, 0, st>>>(pidx, pscore, splits, rows, topk, out_idx, out_score, user_list, user_count, 0, rows);
+    HALS_LAUNCH_CHECK();
+  }
+  if (n_users > rows) {   // overflow of the split region (more than 2048 unproven users): unsplit, one tile per CTA
+    A.list_begin = rows; A.list_end = n_users; A.row_stride = n_users - rows;
+    fill_split(A, n_items, 1);
+    int64_t g2 = (n_users - rows + kScUsers - 1) / kScUsers;
+    if (g2 > 4 * sm_count()) g2 = 4 * sm_count();
+    // candidate rows of the overflow live in the plain (unsplit) SIMT workspace that follows the list region
+    uint64_t* cand2 = (uint64_t*)((uint8_t*)workspace + score_simt_list_workspace_bytes(n_users, n_items, topk));
+    if (int rc = launch_simt_topk_cap(cap, A, dim3((unsigned)g2, 1), smem, extrema, w_als, w_tt, topk, item_offset,
+                                      cand2, out_idx, out_score, st)) return rc;
+  }
+  return 0;
+}
+
+}  // namespace hals
 
 extern "C" int hals_topk_merge(const int32_t* part_idx, const float* part_score, int n_parts,
                                int64_t n_users, int topk, int32_t* out_idx, float* out_score, void* stream) {

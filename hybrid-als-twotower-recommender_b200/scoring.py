@@ -96,13 +96,28 @@ class HybridScorer:
         it = (None, 0) if self.It is None else (nat.ptr(self.It), self.It.stride(0))
         return ua, uas, ia[0], ia[1], self.ka, ut, uts, it[0], it[1], self.kt
 
+    def _workspace(self, n_users: int, k: int) -> torch.Tensor:
+        need = int(nat.lib().hals_score_workspace_bytes(n_users, self.n_items, self.ka, self.kt, k))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def flagged_users(self, n_users: int, k: int) -> int:
+        """Users of the last call (same n_users, k) that the tensor-core path re-ran exactly; -1 if the call
+        took the CUDA-core path."""
+        off = int(nat.lib().hals_score_flag_counter_offset(n_users, self.n_items, self.ka, self.kt, k))
+        if off < 0 or self._ws is None:
+            return -1
+        return int(self._ws[off:off + 4].view(torch.int32).item())
+
     def extrema(self, u0: int = 0, u1: int | None = None) -> torch.Tensor:
         """[U,4] = (min_als, max_als, min_tt, max_tt) per user over ALL items (all shards)."""
         L = nat.lib()
         u1 = self.n_users if u1 is None else u1
         ex = torch.empty((u1 - u0, 4), dtype=torch.float32, device=self.device)
-        nat.check(L.hals_score_extrema(*self._ops(u0, u1), u1 - u0, self.n_items, nat.ptr(ex),
-                                       nat.current_stream()), "hals_score_extrema")
+        ws = self._workspace(u1 - u0, 0)
+        nat.check(L.hals_score_extrema(*self._ops(u0, u1), u1 - u0, self.n_items, nat.ptr(ex), nat.ptr(ws),
+                                       ws.numel(), nat.current_stream()), "hals_score_extrema")
         ex = reduce_extrema(ex, self.world)
         return ex
 
@@ -111,9 +126,7 @@ class HybridScorer:
         L = nat.lib()
         u1 = self.n_users if u1 is None else u1
         n = u1 - u0
-        need = int(L.hals_score_workspace_bytes(n, self.n_items, self.ka, self.kt, k))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._workspace(n, k)
         idx = torch.empty((n, k), dtype=torch.int32, device=self.device)
         sc = torch.empty((n, k), dtype=torch.float32, device=self.device)
         nat.check(L.hals_score_blend_topk(*self._ops(u0, u1), n, self.n_items, nat.ptr(extrema), float(w_als),

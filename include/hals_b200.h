@@ -174,9 +174,14 @@ int hals_tower_item(const hals_tower_weights* w, const int32_t* item_ids,
 int hals_score_extrema(const float* Ua, int64_t ua_stride, const float* Ia, int64_t ia_stride,
                        int ka, const float* Ut, int64_t ut_stride, const float* It,
                        int64_t it_stride, int kt, int64_t n_users, int64_t n_items,
-                       float* extrema /* [n_users,4] */, void* stream);
+                       float* extrema /* [n_users,4] */, void* workspace, size_t workspace_bytes, void* stream);
 
+/* workspace for either entry point (pass topk = 0 for hals_score_extrema alone) */
 size_t hals_score_workspace_bytes(int64_t n_users, int64_t n_items, int ka, int kt, int topk);
+/* Byte offset, inside the workspace, of an int32 holding how many users of the LAST call the tensor-core
+ * path could not prove exact and re-ran on the exact CUDA-core kernel; -1 when the call shape takes the
+ * CUDA-core path altogether.  Diagnostic only. */
+int64_t hals_score_flag_counter_offset(int64_t n_users, int64_t n_items, int ka, int kt, int topk);
 int hals_score_blend_topk(const float* Ua, int64_t ua_stride, const float* Ia, int64_t ia_stride,
                           int ka, const float* Ut, int64_t ut_stride, const float* It,
                           int64_t it_stride, int kt, int64_t n_users, int64_t n_items,

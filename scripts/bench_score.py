@@ -1,0 +1,35 @@
+"""Hybrid scoring micro-benchmark: pass 1 (extrema) + pass 2 (blend + top-k), device resident."""
+import sys, os, time, json, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hybrid_als_twotower_recommender_b200
+from hybrid_als_twotower_recommender_b200 import scoring, _native as nat
+U = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+I = int(sys.argv[2]) if len(sys.argv) > 2 else 1_250_000
+k = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+ka, kt = 128, 50
+g = torch.Generator(device="cuda").manual_seed(1)
+Ua = torch.randn(U, ka, device="cuda", generator=g) * ka ** -0.5
+Ia = torch.randn(I, ka, device="cuda", generator=g)
+Ut = torch.nn.functional.layer_norm(torch.randn(U, kt, device="cuda", generator=g), (kt,))
+It = torch.nn.functional.layer_norm(torch.randn(I, kt, device="cuda", generator=g), (kt,))
+sc = scoring.HybridScorer(Ua, Ia, Ut, It)
+ev = lambda: torch.cuda.Event(enable_timing=True)
+for rep in range(int(os.environ.get('REPS', '3'))):
+    e0, e1, e2 = ev(), ev(), ev()
+    e0.record(); ex = sc.extrema(); e1.record(); idx, s = sc.topk_local(ex, k, 0.8, 0.2); e2.record()
+    torch.cuda.synchronize()
+    t1, t2 = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    f1, f2 = sc.flagged_users(U, 0), sc.flagged_users(U, k)
+    pairs = U * I
+    print(json.dumps({"U": U, "I": I, "k": k, "ms_extrema": t1, "ms_topk": t2, "pairs_per_s": pairs / ((t1 + t2) * 1e-3),
+                      "tflops_pass1": pairs * 2 * (ka + kt) / (t1 * 1e-3) / 1e12, "tflops_pass2": pairs * 2 * (ka + kt) / (t2 * 1e-3) / 1e12,
+                      "flagged_pass2": f2}))
+# spot check against fp64 on a few users
+sel = torch.arange(0, U, max(U // 4, 1), device="cuda")[:4]
+Sa = (Ua[sel].double() @ Ia.double().T); St = (Ut[sel].double() @ It.double().T)
+mm = lambda S: (S - S.min(1, keepdim=True).values) / (S.max(1, keepdim=True).values - S.min(1, keepdim=True).values)
+B = 0.8 * mm(Sa) + 0.2 * mm(St)
+top = torch.topk(B, k, dim=1)
+got = idx[sel].long()
+same = [(len(set(got[j].tolist()) & set(top.indices[j].tolist()))) for j in range(len(sel))]
+print("spot check overlap of top-k sets:", same, "max |score diff|", float((s[sel].double() - torch.gather(B, 1, got)).abs().max()))
