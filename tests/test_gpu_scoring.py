@@ -57,6 +57,51 @@ def test_blend_topk_matches_oracle(U, I, ka, kt, k):
     check_topk_against_dense(B, idx.cpu().numpy(), s.cpu().numpy(), k, TOL * 5)
 
 
+@pytest.mark.parametrize("U,I,ka,kt,k", [(300, 20000, 128, 50, 100), (1000, 5000, 10, 50, 5), (130, 40000, 64, 50, 10),
+                                         (2000, 3000, 128, 50, 100), (5, 900000, 128, 50, 100), (257, 16500, 20, 50, 30)])
+def test_tensor_core_path_matches_oracle(U, I, ka, kt, k):
+    """Shapes large enough for the tcgen05 path (TMA-staged bf16 operands, fused selection epilogue, exact
+    fp32 re-scoring): the result must still be the exact fp32 answer."""
+    _, nat, scoring = _pkg()
+    rng = np.random.default_rng(U * 7 + I)
+    Ua, Ia = rng.normal(0, ka ** -0.5, (U, ka)).astype(np.float32), rng.normal(0, 1, (I, ka)).astype(np.float32)
+    Ut, It = rng.normal(0, 1, (U, kt)).astype(np.float32), rng.normal(0, 1, (I, kt)).astype(np.float32)
+    sc = scoring.HybridScorer(dev(Ua), dev(Ia), dev(Ut), dev(It))
+    assert int(nat.lib().hals_score_flag_counter_offset(U, I, ka, kt, k)) >= 0, "expected the tensor-core path"
+    ex = sc.extrema().cpu().numpy()
+    B, Sa, St = dense_blend(Ua, Ia, Ut, It, 0.2, 0.8)
+    want_ex = np.stack([Sa.min(1), Sa.max(1), St.min(1), St.max(1)], 1)
+    assert np.allclose(ex, want_ex, rtol=1e-5, atol=2e-5)
+    idx, s = sc.recommend(k, 0.2, 0.8)
+    check_topk_against_dense(B, idx.cpu().numpy(), s.cpu().numpy(), k, TOL * 5)
+    assert sc.flagged_users(U, k) <= max(2, U // 20), "the candidate margin should make exact re-runs rare"
+
+
+def test_tensor_core_path_falls_back_exactly_when_bf16_cannot_separate():
+    """Items that differ by less than bf16 resolution: the verification must refuse the tensor-core
+    candidates and the exact re-run must still produce the oracle answer (incl. a constant model)."""
+    _, nat, scoring = _pkg()
+    rng = np.random.default_rng(3)
+    U, I, ka, kt, k = 40, 6000, 16, 8, 10
+    base_a, base_t = rng.normal(0, 1, (1, ka)), rng.normal(0, 1, (1, kt))
+    Ia = (base_a + 3e-3 * rng.normal(0, 1, (I, ka))).astype(np.float32)
+    It = (base_t + 3e-3 * rng.normal(0, 1, (I, kt))).astype(np.float32)
+    Ua, Ut = rng.normal(0, 1, (U, ka)).astype(np.float32), rng.normal(0, 1, (U, kt)).astype(np.float32)
+    Ut[:5] = 0.0                                     # tower score constant (0) for these users: zero range
+    # enough pairs for the tensor-core path
+    reps = 20
+    Ua, Ut = np.tile(Ua, (reps, 1)), np.tile(Ut, (reps, 1))
+    sc = scoring.HybridScorer(dev(Ua), dev(Ia), dev(Ut), dev(It))
+    assert int(nat.lib().hals_score_flag_counter_offset(U * reps, I, ka, kt, k)) >= 0
+    ex = sc.extrema().cpu().numpy()
+    B, Sa, St = dense_blend(Ua, Ia, Ut, It, 0.8, 0.2)
+    assert np.allclose(ex, np.stack([Sa.min(1), Sa.max(1), St.min(1), St.max(1)], 1), rtol=1e-5, atol=1e-5)
+    idx, s = sc.recommend(k, 0.8, 0.2)
+    assert sc.flagged_users(U * reps, k) > 0, "this input must trigger the exact re-run"
+    # score ranges are ~1e-2 here, so fp32 cancellation in (s - min)/(max - min) costs ~1e-5 of the [0,1] range
+    check_topk_against_dense(B, idx.cpu().numpy(), s.cpu().numpy(), k, 2e-4)
+
+
 def test_reference_fixtures_through_fused_kernels():
     """Score lists from the reference fixtures are fed as rank-1 'factors' (u=[1], item=[score]) so
     the fused extrema + blend + top-k kernels see exactly the reference's inputs."""
