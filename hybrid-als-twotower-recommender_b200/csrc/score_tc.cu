@@ -252,53 +252,80 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
       umma::fence_after_sync();
       const int64_t it0 = i_begin + (int64_t)t * BN;
       const bool ragged = it0 + BN > i_end;             // only the last tile of a range
-#pragma unroll 1
-      for (int c0 = half * HB; c0 < (half + 1) * HB; c0 += 32) {
-        if (PASS == 1) {
-          float va[32], vt[32];
-          umma::tmem_ld32(tq + buf * BUFCOLS + c0, va);
-          umma::tmem_ld32(tq + buf * BUFCOLS + BN + c0, vt);
-          // group extremes first (max / min trees); the per-column code runs only when one of the four
+      // software pipeline over the 32-column groups of this warp's half: the tcgen05.ld of group g+1 is in
+      // flight while group g is filtered
+      const uint32_t tbase = tq + buf * BUFCOLS;
+      constexpr int G = HB / 32;
+      if (PASS == 1) {
+        float va[2][32], vt[2][32];
+        umma::tmem_ld32_issue(tbase + half * HB, va[0]);
+        umma::tmem_ld32_issue(tbase + BN + half * HB, vt[0]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int c0 = half * HB + g * 32;
+          umma::tmem_wait_ld_dep(va[g & 1]);
+          umma::tmem_wait_ld_dep(vt[g & 1]);
+          if (g + 1 < G) {
+            umma::tmem_ld32_issue(tbase + c0 + 32, va[(g + 1) & 1]);
+            umma::tmem_ld32_issue(tbase + BN + c0 + 32, vt[(g + 1) & 1]);
+          }
+          const float (&a32)[32] = va[g & 1];
+          const float (&t32)[32] = vt[g & 1];
+          // group extremes first (FMNMX3 chains); the per-column code runs only when one of the four
           // candidate lists can actually change (about 0.5% of the groups per thread)
-          float mxa = va[0], mna = va[0], mxt = vt[0], mnt = vt[0];
+          float mxa = a32[0], mna = a32[0], mxt = t32[0], mnt = t32[0];
 #pragma unroll
           for (int c = 1; c < 32; ++c) {
-            mxa = fmaxf(mxa, va[c]); mna = fminf(mna, va[c]);
-            mxt = fmaxf(mxt, vt[c]); mnt = fminf(mnt, vt[c]);
+            mxa = fmaxf(mxa, a32[c]); mna = fminf(mna, a32[c]);
+            mxt = fmaxf(mxt, t32[c]); mnt = fminf(mnt, t32[c]);
           }
           if (live && (mxa > xv[0][kStExC - 1] || -mna > xv[1][kStExC - 1] || mxt > xv[2][kStExC - 1] || -mnt > xv[3][kStExC - 1])) {
-#pragma unroll 1
-            for (int c = 0; c < 32; ++c) {
-              const float a = select32(va, c), tt = select32(vt, c);
-              if (a > xv[0][kStExC - 1] || -a > xv[1][kStExC - 1] || tt > xv[2][kStExC - 1] || -tt > xv[3][kStExC - 1]) {
-                const int64_t i = it0 + c0 + c;
-                if (!ragged || i < i_end) {
-                  const int gi = (int)i;
-                  insert4(xv[0], xi[0], a, gi);
-                  insert4(xv[1], xi[1], -a, gi);
-                  insert4(xv[2], xi[2], tt, gi);
-                  insert4(xv[3], xi[3], -tt, gi);
-                }
+            // which columns can enter a list: branch-free bitmask, then visit only the set bits (usually one)
+            unsigned m = 0;
+            const float t0 = xv[0][kStExC - 1], t1 = xv[1][kStExC - 1], t2 = xv[2][kStExC - 1], t3 = xv[3][kStExC - 1];
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              m |= ((a32[c] > t0 || -a32[c] > t1 || t32[c] > t2 || -t32[c] > t3) ? 1u : 0u) << c;
+            while (m) {
+              const int c = __ffs(m) - 1;
+              m &= m - 1;
+              const int64_t i = it0 + c0 + c;
+              if (!ragged || i < i_end) {
+                const float a = select32(a32, c), tt = select32(t32, c);
+                const int gi = (int)i;
+                insert4(xv[0], xi[0], a, gi);
+                insert4(xv[1], xi[1], -a, gi);
+                insert4(xv[2], xi[2], tt, gi);
+                insert4(xv[3], xi[3], -tt, gi);
               }
             }
           }
-        } else {
-          float v[32];
-          umma::tmem_ld32(tq + buf * BUFCOLS + c0, v);
-          // Common case: nothing in these 32 columns beats the row threshold -> one binary max tree
-          // (31 FMNMX) and one compare.  Survivors are ~0.2% of the items, so a thread rarely has one, and
-          // almost never two: the single survivor is located by descending the tree; only if the runner-up
-          // also beats the threshold does the full bitmask path run.
-          float l1[16], l2[8], l3[4];
+        }
+      } else {
+        float vv[2][32];
+        umma::tmem_ld32_issue(tbase + half * HB, vv[0]);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) l1[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+        for (int g = 0; g < G; ++g) {
+          const int c0 = half * HB + g * 32;
+          umma::tmem_wait_ld_dep(vv[g & 1]);
+          if (g + 1 < G) umma::tmem_ld32_issue(tbase + c0 + 32, vv[(g + 1) & 1]);
+          const float (&v)[32] = vv[g & 1];
+          // Common case: nothing in these 32 columns beats the row threshold -> one FMNMX3 chain and one
+          // compare.  Survivors are ~0.2% of the items, so a thread rarely has one and almost never two: the
+          // single survivor is located by a max tree + descent; only if the runner-up also beats the threshold
+          // does the full bitmask path run.
+          float gmax = v[0];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) l2[i] = fmaxf(l1[2 * i], l1[2 * i + 1]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) l3[i] = fmaxf(l2[2 * i], l2[2 * i + 1]);
-          const float l40 = fmaxf(l3[0], l3[1]), l41 = fmaxf(l3[2], l3[3]);
-          const float gmax = fmaxf(l40, l41);
+          for (int c = 1; c < 32; ++c) gmax = fmaxf(gmax, v[c]);
           if (gmax > thr) {
+            float l1[16], l2[8], l3[4];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) l1[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) l2[i] = fmaxf(l1[2 * i], l1[2 * i + 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) l3[i] = fmaxf(l2[2 * i], l2[2 * i + 1]);
+            const float l40 = fmaxf(l3[0], l3[1]), l41 = fmaxf(l3[2], l3[3]);
             // descent (ties go left = lower column); `sib` collects the best value NOT on the path
             int ix = l41 > l40;
             float sib = ix ? l40 : l41;
