@@ -25,7 +25,7 @@ class AlsPlan(ctypes.Structure):
     """struct hals_als_plan (include/hals_b200.h)."""
     _fields_ = [
         ("n_items", c_i64), ("n_long_rows", c_i64), ("n_slots", c_i64),
-        ("seg_len", c_i32), ("reserved", c_i32),
+        ("seg_len", c_i32), ("max_nseg", c_i32),
         ("item_row", c_vp), ("item_begin", c_vp), ("item_len", c_vp), ("item_slot", c_vp),
         ("long_row", c_vp), ("long_slot0", c_vp), ("long_nseg", c_vp),
     ]

@@ -96,7 +96,8 @@ class AlsPlanHandle:
         dev = device if device is not None else shard.colidx.device
         self.dev = {n: torch.from_numpy(a).to(dev) for n, a in h.items()}
         self.struct = nat.AlsPlan(
-            n_items=self.n_items, n_long_rows=self.n_long, n_slots=self.n_slots, seg_len=self.seg_len, reserved=0,
+            n_items=self.n_items, n_long_rows=self.n_long, n_slots=self.n_slots, seg_len=self.seg_len,
+            max_nseg=int(h["long_nseg"][: self.n_long].max()) if self.n_long else 0,
             **{n: self.dev[n].data_ptr() for n in h})
         self.workspace_bytes = int(L.hals_als_workspace_bytes(self.n_slots, k, int(n_src)))
         self.workspace = torch.empty(max(self.workspace_bytes, 16), dtype=torch.uint8, device=dev)

@@ -29,15 +29,21 @@ namespace hals {
 
 constexpr int kTcThreads = 128;
 constexpr int kTcKC = 32;          // ratings per stage
-constexpr int kTcStages = 3;
-constexpr int kTcAhead = kTcStages - 1;
+#ifndef HALS_TC_STAGES
+#define HALS_TC_STAGES 4
+#endif
+#ifndef HALS_TC_AHEAD
+#define HALS_TC_AHEAD 2
+#endif
+constexpr int kTcStages = HALS_TC_STAGES;
+constexpr int kTcAhead = HALS_TC_AHEAD;   // chunks in flight; one spare stage keeps the refill off the MMA-completion wait
 constexpr int kTcK = 64;
 constexpr int kTcRowBytes = 128;   // one 64-wide bf16 MN atom row
 constexpr int kTcBlk = kTcKC * kTcRowBytes;          // 4096: one [KC][64] block
 constexpr int kTcStageBytes = 3 * kTcBlk;            // H | L | R
 constexpr int kTcLD = kTcK + 1;
 constexpr int kTcLDP = 68;                            // published pivot rows: 16-byte aligned rows
-constexpr int kTcS1Floats = 65 * kTcLDP;
+constexpr int kTcS1Floats = 3 * kTcLDP;              // two pivot-row slots + the x hand-over row
 constexpr int kTcTmemCols = 128;
 constexpr int kTcN = 80;
 
@@ -156,7 +162,7 @@ __device__ __forceinline__ float ldlt64_rows(f32x2 (&ap)[32], float rhs, uint32_
 #define HALS_LDLT_STEP(NPAIRS, SYNC)                                                                  \
   {                                                                                                   \
     const int j = 8 * b + jj;                                                                         \
-    const uint32_t Pj = P + j * LDP * 4;                                                              \
+    const uint32_t Pj = P + (j & 1) * LDP * 4;   /* pivot rows are dead after their step: 2 slots */   \
     const float aj = (jj & 1) ? hi2(ap[jj / 2]) : lo2(ap[jj / 2]);                                    \
     const bool own = (m == j);                                                                        \
     const float inv = __fdividef(1.0f, aj);                                                           \
@@ -211,7 +217,7 @@ __device__ __forceinline__ float ldlt64_rows(f32x2 (&ap)[32], float rhs, uint32_
   // ---- back substitution ------------------------------------------------------------------------
   float acc = rhs;
   float x = 0.f;
-  const uint32_t X = P + 64 * LDP * 4;                   // x_32..x_63 handed from warp 1 to warp 0
+  const uint32_t X = P + 2 * LDP * 4;                    // x_32..x_63 handed from warp 1 to warp 0
   if (m >= 32) {
 #pragma unroll
     for (int j = 63; j >= 32; --j) {
@@ -439,6 +445,61 @@ als_tc64_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ va
   if (warp == 0) umma::tmem_dealloc(tmem, kTcTmemCols);
 }
 
+// Long rows, level 1 of the deterministic slot reduction: groups of kSlotGroup consecutive slots of one row
+// are summed (fixed order) into the group's first slot; a Zipf-head row with hundreds of slices would otherwise
+// be summed by a single CTA.  grid = (n_long_rows, ceil(max_nseg / kSlotGroup)).
+constexpr int kSlotGroup = 16;
+__global__ void __launch_bounds__(256)
+als_slot_group_sum_kernel(float* __restrict__ workspace, const int32_t* __restrict__ long_slot0,
+                          const int32_t* __restrict__ long_nseg, int slot_floats) {
+  const int ns = long_nseg[blockIdx.x];
+  const int g0 = blockIdx.y * kSlotGroup;
+  if (g0 >= ns || ns <= kSlotGroup) return;            // short lists are summed by the solve kernel directly
+  const int g1 = min(ns, g0 + kSlotGroup);
+  float* base = workspace + (size_t)(long_slot0[blockIdx.x] + g0) * slot_floats;
+  for (int e = threadIdx.x; e < slot_floats; e += 256) {
+    float s = base[e];
+    for (int q = 1; q < g1 - g0; ++q) s += base[(size_t)q * slot_floats + e];
+    base[e] = s;
+  }
+}
+
+// Long rows (rank 64): sums the per-slice partial (A, b, n) slots in slot order -- deterministic -- adds the
+// ridge and solves with the same register-resident LDL^T as the main kernel.  One 64-thread CTA per long row.
+__global__ void __launch_bounds__(64)
+als_reduce_solve64_kernel(const float* __restrict__ workspace, float* __restrict__ dst, float reg,
+                          const int32_t* __restrict__ long_row, const int32_t* __restrict__ long_slot0,
+                          const int32_t* __restrict__ long_nseg) {
+  constexpr int K = kTcK, LDP = kTcLDP;
+  __shared__ __align__(16) float P[3 * kTcLDP];
+  const int m = threadIdx.x;
+  const int row = long_row[blockIdx.x];
+  const int s0 = long_slot0[blockIdx.x], ns = long_nseg[blockIdx.x];
+  const size_t sf = (size_t)K * K + K + 4;
+  float a[65];
+#pragma unroll
+  for (int n = 0; n < 65; ++n) a[n] = 0.f;
+  float cnt = 0.f;
+  const int stride = ns > kSlotGroup ? kSlotGroup : 1;  // rows with many slices were pre-summed per group
+  for (int q = 0; q < ns; q += stride) {
+    const float* W = workspace + (size_t)(s0 + q) * sf;
+#pragma unroll
+    for (int n = 0; n < 64; n += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(W + m * K + n);
+      a[n] += v.x; a[n + 1] += v.y; a[n + 2] += v.z; a[n + 3] += v.w;
+    }
+    a[64] += W[K * K + m];
+    cnt += W[K * K + K];
+  }
+  const float lam = reg * cnt;
+  f32x2 ap[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    ap[i] = pack2(a[2 * i] + (2 * i == m ? lam : 0.f), a[2 * i + 1] + (2 * i + 1 == m ? lam : 0.f));
+  const float x = ldlt64_rows<LDP>(ap, a[64], umma::smem_u32(P), m);
+  dst[(int64_t)row * K + m] = x;
+}
+
 int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* src, int64_t n_src, float* dst,
                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st) {
   __nv_bfloat16* hl = reinterpret_cast<__nv_bfloat16*>(split_buf);
@@ -454,7 +515,17 @@ int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* sr
                                                              plan->item_begin, plan->item_len, plan->item_slot,
                                                              plan->n_items, slots, sm_count());
   HALS_LAUNCH_CHECK();
-  return als_launch_reduce_solve(slots, dst, kTcK, reg, nullptr, plan, st);
+  if (plan->n_long_rows > 0) {
+    if (plan->max_nseg > kSlotGroup) {
+      dim3 g((unsigned)plan->n_long_rows, (unsigned)((plan->max_nseg + kSlotGroup - 1) / kSlotGroup));
+      als_slot_group_sum_kernel<<<g, 256, 0, st>>>(slots, plan->long_slot0, plan->long_nseg, kTcK * kTcK + kTcK + 4);
+      HALS_LAUNCH_CHECK();
+    }
+    als_reduce_solve64_kernel<<<(unsigned)plan->n_long_rows, 64, 0, st>>>(slots, dst, reg, plan->long_row,
+                                                                          plan->long_slot0, plan->long_nseg);
+    HALS_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 }  // namespace hals

@@ -1,5 +1,6 @@
 // C-ABI glue: error state, launch counter, host-side ALS planner, half-step dispatch.
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -68,10 +69,13 @@ extern "C" int hals_als_plan_fill_host(const int64_t* rowptr_host, int64_t m, in
                                        int32_t* long_nseg) {
   HALS_REQUIRE(rowptr_host && item_row && item_begin && item_len && item_slot, "null pointer");
   HALS_REQUIRE(seg_len >= 32, "seg_len must be >= 32");
-  int64_t it = 0, lr = 0, slot = 0;
-  for (int64_t j = 0; j < m; ++j) {  // pass 1: long rows
+  struct Item { int32_t row; int64_t begin; int32_t len; int32_t slot; };
+  std::vector<Item> segs, rows;
+  int64_t lr = 0, slot = 0;
+  for (int64_t j = 0; j < m; ++j) {
     const int64_t b = rowptr_host[j], len = rowptr_host[j + 1] - b;
-    if (len <= seg_len) continue;
+    if (len == 0) continue;
+    if (len <= seg_len) { rows.push_back({(int32_t)j, b, (int32_t)len, -1}); continue; }
     HALS_REQUIRE(long_row && long_slot0 && long_nseg, "null long-row arrays");
     const int64_t ns = (len + seg_len - 1) / seg_len;
     // equal slices (not seg_len + remainder) so that slice costs are uniform
@@ -80,14 +84,24 @@ extern "C" int hals_als_plan_fill_host(const int64_t* rowptr_host, int64_t m, in
     for (int64_t s = 0; s < ns; ++s) {
       const int64_t o = s * per;
       const int64_t l = (o + per <= len) ? per : len - o;
-      item_row[it] = (int32_t)j; item_begin[it] = b + o; item_len[it] = (int32_t)l;
-      item_slot[it] = (int32_t)slot; ++it; ++slot;
+      segs.push_back({(int32_t)j, b + o, (int32_t)l, (int32_t)slot});
+      ++slot;
     }
   }
-  for (int64_t j = 0; j < m; ++j) {  // pass 2: whole rows
-    const int64_t b = rowptr_host[j], len = rowptr_host[j + 1] - b;
-    if (len == 0 || len > seg_len) continue;
-    item_row[it] = (int32_t)j; item_begin[it] = b; item_len[it] = (int32_t)len; item_slot[it] = -1; ++it;
+  // Emission order.  The kernels walk the items round-robin over a persistent grid (4 CTAs x 148 SMs): a block of
+  // kPlanBlock slices (gather-heavy, nothing to solve) is followed by its share of whole rows (solve-heavy), so
+  // that every CTA alternates between the two and its solver warps work while its producers gather a slice.
+  // With fewer than one block of slices this degenerates to "slices first, then rows".
+  constexpr int64_t kPlanBlock = 592;
+  const int64_t nblk = segs.empty() ? 1 : ((int64_t)segs.size() + kPlanBlock - 1) / kPlanBlock;
+  const int64_t rows_per_blk = ((int64_t)rows.size() + nblk - 1) / nblk;
+  int64_t it = 0;
+  auto emit = [&](const Item& x) {
+    item_row[it] = x.row; item_begin[it] = x.begin; item_len[it] = x.len; item_slot[it] = x.slot; ++it;
+  };
+  for (int64_t b = 0; b < nblk; ++b) {
+    for (int64_t s = b * kPlanBlock; s < (b + 1) * kPlanBlock && s < (int64_t)segs.size(); ++s) emit(segs[s]);
+    for (int64_t r = b * rows_per_blk; r < (b + 1) * rows_per_blk && r < (int64_t)rows.size(); ++r) emit(rows[r]);
   }
   return 0;
 }

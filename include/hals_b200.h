@@ -64,7 +64,7 @@ typedef struct hals_als_plan {
   int64_t n_long_rows;       /* rows cut into >1 segment                                   */
   int64_t n_slots;           /* partial (A,b) slots needed in the workspace                */
   int32_t seg_len;           /* segment length the plan was built for                      */
-  int32_t reserved;
+  int32_t max_nseg;          /* largest entry of long_nseg (0 when there are no long rows)  */
   const int32_t* item_row;   /* [n_items] destination row                                  */
   const int64_t* item_begin; /* [n_items] first rating (index into colidx/vals)            */
   const int32_t* item_len;   /* [n_items] ratings in this item                             */
