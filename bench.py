@@ -85,7 +85,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -125,36 +125,49 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port on a bounded row sample
 # ------------------------------------------------------------------------------------------
-def cpu_baseline_run(w, u, i, r, target_nnz=1_500_000, seed=3):
-    from oracle import als_oracle, c_oracle
-    U, I, k = w["users"], w["items"], w["rank"]
-    t0 = time.time()
-    X = als_oracle.init_factors(U, k, seed)
-    ir, ic, iv = als_oracle.coo_to_csr(i, u, r, I)
-    ur, uc, uv = als_oracle.coo_to_csr(u, i, r, U)
+class CpuBaseline:
+    """The CPU oracle port timed on a bounded row sample of the workload (CSR built once, outside the timing)."""
 
-    def sample_rows(rowptr, n):
-        mid = n // 3
-        end = int(np.searchsorted(rowptr, rowptr[mid] + min(target_nnz, rowptr[-1] - rowptr[mid])))
-        end = max(min(end, n), mid + 1)
-        return mid, end, int(rowptr[end] - rowptr[mid])
+    def __init__(self, w, u, i, r, target_nnz, seed=3):
+        from oracle import als_oracle
+        self.w = w
+        U, I, k = w["users"], w["items"], w["rank"]
+        t0 = time.time()
+        self.X = als_oracle.init_factors(U, k, seed)
+        self.Yfull = als_oracle.init_factors(I, k, seed + 1)
+        self.item_csr = als_oracle.coo_to_csr(i, u, r, I)
+        self.user_csr = als_oracle.coo_to_csr(u, i, r, U)
 
-    ib, ie, inz = sample_rows(ir, I)
-    ub, ue, unz = sample_rows(ur, U)
-    prep = time.time() - t0
-    Y = np.zeros((I, k), np.float32)
-    t0 = time.time()
-    c_oracle.als_half_step(ir, ic, iv, X, w["reg"], row_begin=ib, row_end=ie, out=Y)
-    ti = time.time() - t0
-    Yfull = als_oracle.init_factors(I, k, seed + 1)
-    t0 = time.time()
-    c_oracle.als_half_step(ur, uc, uv, Yfull, w["reg"], row_begin=ub, row_end=ue)
-    tu = time.time() - t0
-    per_rating = ti / max(inz, 1) + tu / max(unz, 1)          # seconds per rating per sweep
-    return {"value": 1.0 / per_rating, "unit": UNIT, "cores": c_oracle.num_threads(), "kind": "port",
-            "sample": f"item rows [{ib},{ie}) = {inz} ratings in {ti:.2f}s + user rows [{ub},{ue}) = {unz} ratings "
-                      f"in {tu:.2f}s of the {w['nnz']}-rating workload (C oracle, fp64 packed dspr + dppsv, OpenMP); "
-                      f"Spark local[N] unavailable offline", "prep_s": round(prep, 2)}
+        def sample_rows(rowptr, n):
+            mid = n // 3
+            end = int(np.searchsorted(rowptr, rowptr[mid] + min(target_nnz, rowptr[-1] - rowptr[mid])))
+            end = max(min(end, n), mid + 1)
+            return mid, end, int(rowptr[end] - rowptr[mid])
+
+        self.isel = sample_rows(self.item_csr[0], I)
+        self.usel = sample_rows(self.user_csr[0], U)
+        self.prep_s = time.time() - t0
+
+    def run(self):
+        from oracle import c_oracle
+        w = self.w
+        (ib, ie, inz), (ub, ue, unz) = self.isel, self.usel
+        Y = np.zeros((w["items"], w["rank"]), np.float32)
+        t0 = time.time()
+        c_oracle.als_half_step(*self.item_csr, self.X, w["reg"], row_begin=ib, row_end=ie, out=Y)
+        ti = time.time() - t0
+        t0 = time.time()
+        c_oracle.als_half_step(*self.user_csr, self.Yfull, w["reg"], row_begin=ub, row_end=ue)
+        tu = time.time() - t0
+        per_rating = ti / max(inz, 1) + tu / max(unz, 1)          # seconds per rating per sweep
+        return {"value": 1.0 / per_rating, "unit": UNIT, "cores": c_oracle.num_threads(), "kind": "port",
+                "sample": f"item rows [{ib},{ie}) = {inz} ratings in {ti:.2f}s + user rows [{ub},{ue}) = {unz} ratings "
+                          f"in {tu:.2f}s of the {w['nnz']}-rating workload (C oracle, fp64 packed dspr + dppsv, OpenMP); "
+                          f"Spark local[N] unavailable offline", "prep_s": round(self.prep_s, 2)}
+
+
+def cpu_baseline_run(w, u, i, r, target_nnz=15_000_000, seed=3):
+    return CpuBaseline(w, u, i, r, target_nnz, seed).run()
 
 
 def run_reference(args, w):
@@ -167,8 +180,9 @@ def run_reference(args, w):
     u, i, r = u.numpy(), i.numpy(), r.numpy()
     vals = []
     res = None
+    cb = CpuBaseline(w, u, i, r, args.cpu_sample)
     for s in range(args.warmup + args.steps):
-        res = cpu_baseline_run(w, u, i, r, target_nnz=args.cpu_sample)
+        res = cb.run()
         if s >= args.warmup:
             vals.append(res["value"])
     v = float(np.mean(vals))
@@ -242,7 +256,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-sweeps", type=int, default=10, help="sweeps per end-to-end train()-shaped call")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=1_500_000, help="ratings per half-step in the CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=15_000_000, help="ratings per half-step in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     ap.add_argument("--no-scoring", action="store_true", help="skip the hybrid top-k scoring leg (extra.hybrid_topk)")
