@@ -146,6 +146,7 @@ __device__ __forceinline__ float ldlt64_rows(f32x2 (&ap)[32], float rhs, uint32_
   // ap[i] = (a[2i], a[2i+1]) of this thread's matrix row; rhs = its right-hand side element (a[64])
   const int lane = m & 31;
   float inv_d = 0.f;
+  float inv_next = __fdividef(1.0f, lo2(ap[0]));
 #ifdef HALS_TC_PROFILE
   long long ts = clock64();
 #define HALS_PFS(i) do { const long long n__ = clock64(); pfs[i] += n__ - ts; ts = n__; } while (0)
@@ -165,7 +166,7 @@ __device__ __forceinline__ float ldlt64_rows(f32x2 (&ap)[32], float rhs, uint32_
     const uint32_t Pj = P + (j & 1) * LDP * 4;   /* pivot rows are dead after their step: 2 slots */   \
     const float aj = (jj & 1) ? hi2(ap[jj / 2]) : lo2(ap[jj / 2]);                                    \
     const bool own = (m == j);                                                                        \
-    const float inv = __fdividef(1.0f, aj);                                                           \
+    const float inv = inv_next;          /* 1/a[j], computed during the previous step's update */     \
     if (own) inv_d = inv;                                                                             \
     _Pragma("unroll") for (int c4 = (jj / 4) * 4; c4 < 2 * (NPAIRS); c4 += 4) {                       \
       f32x2 p0 = ap[c4 / 2], p1 = ap[c4 / 2 + 1];                                                     \
@@ -181,11 +182,15 @@ __device__ __forceinline__ float ldlt64_rows(f32x2 (&ap)[32], float rhs, uint32_
     SYNC;                                                                                             \
     const float nw = (m > j) ? -aj * lds32(Pj + jj * 4) : 0.f;                                        \
     const f32x2 nw2 = pack2(nw, nw);                                                                  \
+    /* the pair holding the NEXT pivot goes first, so its reciprocal overlaps the rest of the update */ \
+    const int pn = (jj + 1) / 2;          /* jj = 7: window register 8 = next block's pivot 0 */        \
+    ap[pn] = ffma2(nw2, lds64x2(Pj + pn * 8), ap[pn]);                                                \
+    inv_next = __fdividef(1.0f, ((jj + 1) & 1) ? hi2(ap[pn]) : lo2(ap[pn]));                          \
     _Pragma("unroll") for (int i = ((jj + 1) / 4) * 2; i < (NPAIRS); i += 2) {                        \
       f32x2 q0, q1;                                                                                   \
       lds128x2(Pj + i * 8, q0, q1);                                                                   \
-      ap[i] = ffma2(nw2, q0, ap[i]);                                                                  \
-      ap[i + 1] = ffma2(nw2, q1, ap[i + 1]);                                                          \
+      if (i != pn) ap[i] = ffma2(nw2, q0, ap[i]);                                                     \
+      if (i + 1 != pn) ap[i + 1] = ffma2(nw2, q1, ap[i + 1]);                                         \
     }                                                                                                 \
     rhs = fmaf(nw, lds32(Pj + 64 * 4), rhs);                                                          \
   }
