@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include "als_common.cuh"
+#include "als_tc_common.cuh"
 #include "umma.cuh"
 
 namespace hals {
@@ -68,64 +69,6 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t n_rows,
   *reinterpret_cast<uint4*>(o + c * 8) = *reinterpret_cast<const uint4*>(h);
   *reinterpret_cast<uint4*>(o + k + c * 8) = *reinterpret_cast<const uint4*>(l);
 }
-
-// Explicit shared-state-space accesses on 32-bit addresses: keeps the solver on LDS/STS (pointer
-// arithmetic through uintptr_t otherwise degrades to generic LD/ST) and halves address registers.
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ float lds32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t addr, float a) {
-  asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(a) : "memory");
-}
-
-// Packed fp32x2 arithmetic (sm_100 FFMA2): two row elements per 64-bit register, one instruction.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;\n" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;\n" : "=f"(a), "=f"(b) : "l"(v)); return b; }
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {   // a * b + c, both halves
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ void lds128x2(uint32_t addr, f32x2& p0, f32x2& p1) {
-  asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];\n" : "=l"(p0), "=l"(p1) : "r"(addr));
-}
-__device__ __forceinline__ f32x2 lds64x2(uint32_t addr) {
-  f32x2 p;
-  asm volatile("ld.shared.b64 %0, [%1];\n" : "=l"(p) : "r"(addr));
-  return p;
-}
-__device__ __forceinline__ void sts128x2(uint32_t addr, f32x2 p0, f32x2 p1) {
-  asm volatile("st.shared.v2.b64 [%0], {%1,%2};\n" ::"r"(addr), "l"(p0), "l"(p1) : "memory");
-}
-
-// Predicated (branch-free) shared stores: the pivot owner publishes without diverging its warp.
-__device__ __forceinline__ void sts128x2_if(bool pred, uint32_t addr, f32x2 p0, f32x2 p1) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.b64 [%0], {%1,%2};\n\t}\n"
-               ::"r"(addr), "l"(p0), "l"(p1), "r"((uint32_t)pred) : "memory");
-}
-__device__ __forceinline__ void sts32_if(bool pred, uint32_t addr, float a) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}\n"
-               ::"r"(addr), "f"(a), "r"((uint32_t)pred) : "memory");
-}
-
-// Named barriers: 1 = the two solver warps, 2 = the two producer warps (0 is __syncthreads).
-__device__ __forceinline__ void bar_sync_64(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
 
 // Register-resident solve of one 64x64 SPD system by the two solver warps (thread m owns row m
 // of the symmetric matrix, a[0..63], and its right-hand side element a[64]).
@@ -211,10 +154,13 @@ __device__ __forceinline__ float ldlt64_rows(f32x2 (&ap)[32], float rhs, uint32_
 #pragma unroll 1
     for (int b = 4; b < 8; ++b) {                        // pivots 32..63: warp 1 alone; live columns fit 16 pairs
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) HALS_LDLT_STEP(16, __syncwarp())
+      for (int jj = 0; jj < 8; ++jj) HALS_LDLT_STEP(16, if (b == 4 && jj == 0) bar_sync_64(3); else __syncwarp())
       HALS_LDLT_ROTATE()
     }
   } else {                                               // warp 0: finish the rotation (4 x 8 columns)
+    // non-blocking arrival on the barrier of pivot 32: warp 0's reads of the 2-slot pivot buffer are over
+    // (barrier 3: a warp must not arrive twice on one generation of barrier 1)
+    asm volatile("bar.arrive 3, 64;\n" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) { const f32x2 tmp = ap[i]; ap[i] = ap[i + 16]; ap[i + 16] = tmp; }
   }
@@ -505,6 +451,22 @@ als_reduce_solve64_kernel(const float* __restrict__ workspace, float* __restrict
   dst[(int64_t)row * K + m] = x;
 }
 
+int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_floats, cudaStream_t st) {
+  if (plan->max_nseg > kSlotGroup) {
+    dim3 g((unsigned)plan->n_long_rows, (unsigned)((plan->max_nseg + kSlotGroup - 1) / kSlotGroup));
+    als_slot_group_sum_kernel<<<g, 256, 0, st>>>(slots, plan->long_slot0, plan->long_nseg, slot_floats);
+    HALS_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int als_launch_split_bf16(const float* src, int64_t n_src, int k, void* out, cudaStream_t st) {
+  const int64_t nthreads = n_src * (k / 8);
+  split_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(src, n_src, k, reinterpret_cast<__nv_bfloat16*>(out));
+  HALS_LAUNCH_CHECK();
+  return 0;
+}
+
 int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* src, int64_t n_src, float* dst,
                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st) {
   __nv_bfloat16* hl = reinterpret_cast<__nv_bfloat16*>(split_buf);
@@ -521,11 +483,7 @@ int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* sr
                                                              plan->n_items, slots, sm_count());
   HALS_LAUNCH_CHECK();
   if (plan->n_long_rows > 0) {
-    if (plan->max_nseg > kSlotGroup) {
-      dim3 g((unsigned)plan->n_long_rows, (unsigned)((plan->max_nseg + kSlotGroup - 1) / kSlotGroup));
-      als_slot_group_sum_kernel<<<g, 256, 0, st>>>(slots, plan->long_slot0, plan->long_nseg, kTcK * kTcK + kTcK + 4);
-      HALS_LAUNCH_CHECK();
-    }
+    if (int rc = als_launch_slot_group_sum(slots, plan, kTcK * kTcK + kTcK + 4, st)) return rc;
     als_reduce_solve64_kernel<<<(unsigned)plan->n_long_rows, 64, 0, st>>>(slots, dst, reg, plan->long_row,
                                                                           plan->long_slot0, plan->long_nseg);
     HALS_LAUNCH_CHECK();

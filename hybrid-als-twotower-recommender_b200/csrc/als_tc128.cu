@@ -1,0 +1,377 @@
+// ALS half-step, tensor-core path for rank 128 (explicit feedback): Netflix-shape config.
+// Same construction as als_tc.cu (bf16 h/l split, tcgen05.mma into TMEM, register-resident
+// square-root-free Cholesky), re-dimensioned for a 128 x 128 system; replaces Spark's
+// NormalEquation.add + CholeskySolver.solve reached from src/als_model.py:62.
+//
+//   per 16 ratings, three instructions on the same gathered [32 ratings][h(128) | l(128)] bf16 stage:
+//     D[:,   0:256] += H^T . [H | L]      (M = 128, N = 256)   -> h h^T (cols 0..127) and h l^T (128..255)
+//     D[:, 256:272] += H^T . R            (M = 128, N = 16)    -> sum h r_hi, sum h r_lo
+//     D[:, 272:288] += L^T . R            (M = 128, N = 16)    -> sum l r_hi
+//   A = D_hh + D_hl + D_hl^T ,  b = D[.,256] + D[.,257] + D[.,272]          (drops l l^T ~ 2^-18)
+//
+// One persistent CTA per SM (the accumulator needs 288 of the 512 TMEM columns), 10 warps:
+//   warps 0,1   producers: cp.async gather into the swizzled MN-major stage ring, one thread issues the MMAs
+//   warps 2-5   solver group A, warps 6-9 solver group B: thread = matrix row = TMEM lane; the groups take
+//               alternate work items, so while one group eliminates (128 dependent pivot steps) the other
+//               drains / eliminates the next row and the producers gather the one after.
+// The elimination is ldlt64_rows' scheme at twice the width: rotating register window (4 pivots per loop
+// iteration), pivot row published to a 2-slot shared buffer, one named barrier per step whose participant
+// count shrinks as warps run out of rows (128 / 96 / 64 threads, then __syncwarp).
+#include <cuda_bf16.h>
+
+#include "als_common.cuh"
+#include "als_tc_common.cuh"
+#include "umma.cuh"
+
+namespace hals {
+
+constexpr int k8K = 128;
+constexpr int k8KC = 32;                    // ratings per stage
+constexpr int k8Stages = 3;
+constexpr int k8Ahead = 2;
+constexpr int k8Blk = k8KC * 128;           // one [KC][64] bf16 block (4 KB)
+constexpr int k8StageBytes = 5 * k8Blk;     // H0 | H1 | L0 | L1 | R
+constexpr int k8Threads = 320;
+constexpr int k8LDH = 129;                  // leading dimension of the h l^T staging buffer
+constexpr int k8LDP = 132;                  // pivot slot: 128 window floats + rhs (+ pad to 16 B)
+constexpr int k8GroupFloats = 128 * k8LDH + 2 * k8LDP + 128;   // HL buffer + 2 pivot slots + x hand-over
+constexpr int k8GroupBytes = (k8GroupFloats * 4 + 15) / 16 * 16;
+constexpr size_t k8SlotFloats = (size_t)k8K * k8K + k8K + 4;
+
+// 128 x 128 SPD solve by one solver group (4 warps, thread = row m, rb = m / 32).
+// ap[i] = (a[2i], a[2i+1]) of the row, rhs = right-hand side element.  Returns x_m.
+__device__ __forceinline__ float ldlt128_rows(f32x2 (&ap)[64], float rhs, uint32_t P, uint32_t X, int m, int bar_base) {
+  const int rb = m >> 5, lane = m & 31;
+  float inv_d = 0.f;
+  float inv_next = __fdividef(1.0f, lo2(ap[0]));
+  // one elimination step at window position jj (0..3) of the current 4-pivot block
+#define HALS_L128_STEP(NPAIRS)                                                                          \
+  {                                                                                                     \
+    const int j = 4 * b4 + jj;                                                                          \
+    const uint32_t Pj = P + (j & 1) * (k8LDP * 4);                                                      \
+    const float aj = (jj & 1) ? hi2(ap[jj / 2]) : lo2(ap[jj / 2]);                                      \
+    const bool own = (m == j);                                                                          \
+    const float inv = inv_next;                                                                         \
+    if (own) inv_d = inv;                                                                               \
+    _Pragma("unroll") for (int c4 = 0; c4 < 2 * (NPAIRS); c4 += 4) {                                    \
+      f32x2 p0 = ap[c4 / 2], p1 = ap[c4 / 2 + 1];                                                       \
+      if (c4 == 0) {                                                                                    \
+        if (jj == 0) p0 = pack2(inv, hi2(p0));                                                          \
+        if (jj == 1) p0 = pack2(lo2(p0), inv);                                                          \
+        if (jj == 2) p1 = pack2(inv, hi2(p1));                                                          \
+        if (jj == 3) p1 = pack2(lo2(p1), inv);                                                          \
+      }                                                                                                 \
+      sts128x2_if(own, Pj + c4 * 4, p0, p1);                                                            \
+    }                                                                                                   \
+    sts32_if(own, Pj + 128 * 4, rhs);                                                                   \
+    /* the first step of a phase also waits for the warp that just ran out of rows: its reads of the   */ \
+    /* 2-slot pivot buffer must be over before the slot is published again                              */ \
+    if (jj == 0 && (b4 & 7) == 0 && ph > 0) bar_sync_n(bar_base + 2 + ph, 160 - 32 * ph);               \
+    else if (ph == 3) __syncwarp();                                                                     \
+    else bar_sync_n(bar_base + ph, 128 - 32 * ph);                                                      \
+    const float nw = (m > j) ? -aj * lds32(Pj + jj * 4) : 0.f;                                          \
+    const f32x2 nw2 = pack2(nw, nw);                                                                    \
+    const int pn = (jj + 1) / 2;          /* jj = 3: window register 4 = next block's pivot 0 */        \
+    ap[pn] = ffma2(nw2, lds64x2(Pj + pn * 8), ap[pn]);                                                  \
+    inv_next = __fdividef(1.0f, ((jj + 1) & 1) ? hi2(ap[pn]) : lo2(ap[pn]));                            \
+    _Pragma("unroll") for (int i = (jj == 3 ? 2 : 0); i < (NPAIRS); i += 2) {                           \
+      f32x2 q0, q1;                                                                                     \
+      lds128x2(Pj + i * 8, q0, q1);                                                                     \
+      if (i != pn) ap[i] = ffma2(nw2, q0, ap[i]);                                                       \
+      if (i + 1 != pn) ap[i + 1] = ffma2(nw2, q1, ap[i + 1]);                                           \
+    }                                                                                                   \
+    rhs = fmaf(nw, lds32(Pj + 128 * 4), rhs);                                                           \
+  }
+#pragma unroll 1
+  for (int b4 = 0; b4 < 32; ++b4) {
+    const int ph = b4 >> 3;                               // pivots 32 ph .. 32 ph + 31 belong to warp ph
+    if (rb < ph) {                                        // this warp has no rows left (warp-uniform)
+      bar_arrive_n(bar_base + 2 + ph, 160 - 32 * ph);     // hand-shake barrier (own id: a warp must not arrive twice
+                                                          // on one barrier generation), see the first-step barrier below
+      break;
+    }
+    if (b4 < 16) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) HALS_L128_STEP(64)
+    } else {                                              // fewer than 64 live columns: half window
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) HALS_L128_STEP(32)
+    }
+    const f32x2 t0 = ap[0], t1 = ap[1];                   // rotate the window by 4 columns
+#pragma unroll
+    for (int i = 0; i < 62; ++i) ap[i] = ap[i + 2];
+    ap[62] = t0; ap[63] = t1;
+  }
+#undef HALS_L128_STEP
+  // A warp leaves the loop after 32 (rb + 1) columns of rotation; 96 more columns bring its own pivot block to
+  // window registers 0..31 and the later columns (the frozen upper part of its rows) to registers 32.. .
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {                          // in-place rotation by 48 pairs: 16 cycles of length 4
+    const f32x2 t = ap[i];
+    ap[i] = ap[i + 48]; ap[i + 48] = ap[i + 32]; ap[i + 32] = ap[i + 16]; ap[i + 16] = t;
+  }
+  // ---- back substitution: x_c = (y_c - sum_{j>c} a_c[j] x_j) / d_c, last warp first ---------------------
+  float acc = rhs, x = 0.f;
+#pragma unroll 1
+  for (int w = 3; w >= 0; --w) {
+    if (rb == w) {
+      // contributions of the already solved x_j, j >= 32 (rb + 1): window registers 32 .. 127 - 32 rb
+#pragma unroll
+      for (int r4 = 32; r4 < 128; r4 += 4) {
+        if (r4 < 128 - 32 * rb) {
+          const float4 q = lds128(X + (32 * rb + r4) * 4);
+          acc = fmaf(-lo2(ap[r4 / 2]), q.x, acc);
+          acc = fmaf(-hi2(ap[r4 / 2]), q.y, acc);
+          acc = fmaf(-lo2(ap[r4 / 2 + 1]), q.z, acc);
+          acc = fmaf(-hi2(ap[r4 / 2 + 1]), q.w, acc);
+        }
+      }
+#pragma unroll
+      for (int jl = 31; jl >= 0; --jl) {                  // own block: pivot 32 rb + jl lives in lane jl
+        const float xj = __shfl_sync(0xffffffffu, acc * inv_d, jl);
+        if (lane == jl) x = xj;
+        const float aj = (jl & 1) ? hi2(ap[jl / 2]) : lo2(ap[jl / 2]);
+        if (lane < jl) acc = fmaf(-aj, xj, acc);
+      }
+      sts32(X + m * 4, x);
+    }
+    if (w > 0) bar_sync_n(bar_base, 128);
+  }
+  return x;
+}
+
+__global__ void __launch_bounds__(k8Threads, 1)
+als_tc128_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                 const __nv_bfloat16* __restrict__ src_hl, float* __restrict__ dst, float reg,
+                 const int32_t* __restrict__ item_row, const int64_t* __restrict__ item_begin,
+                 const int32_t* __restrict__ item_len, const int32_t* __restrict__ item_slot,
+                 int64_t n_items, float* __restrict__ workspace) {
+  constexpr int K = k8K, KC = k8KC;
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ uint64_t mbar_free[k8Stages];
+  __shared__ uint64_t mbar_acc[2];        // accumulator complete, one per solver group
+  __shared__ uint64_t mbar_tmem_free;     // accumulator drained
+  __shared__ uint32_t tmem_slot;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp < 2;
+  const int group = producer ? -1 : (warp - 2) >> 2;
+  const int m = 32 * (warp & 3) + lane;                 // solver: matrix row == TMEM lane
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int s = 0; s < k8Stages; ++s) umma::mbar_init(&mbar_free[s], 1);
+    umma::mbar_init(&mbar_acc[0], 1);
+    umma::mbar_init(&mbar_acc[1], 1);
+    umma::mbar_init(&mbar_tmem_free, 1);
+    umma::mbar_fence_init();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sbase = umma::smem_u32(base);
+
+  if (producer) {
+    // ================================================================ producers
+    constexpr uint32_t idesc256 = umma::make_instr_desc(umma::kFmtBF16, true, true, 128, 256);
+    constexpr uint32_t idesc16 = umma::make_instr_desc(umma::kFmtBF16, true, true, 128, 16);
+    const int t_sub = tid >> 5, piece = tid & 31;        // 2 rating rows per pass, 32 x 16-byte pieces per 512 B row
+    const int blk_off = (piece >> 3) * k8Blk, chunk = piece & 7;
+    uint32_t g = 0, it = 0;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int64_t begin = item_begin[item];
+      const int len = item_len[item];
+      const int nc = (len + KC - 1) / KC;
+      auto fetch_idx = [&](int c, int& ci, float& rv) {
+        const int q = c * KC + lane;
+        const bool ok = q < len;
+        ci = ok ? __ldg(colidx + begin + q) : -1;
+        rv = (ok && warp == 0) ? __ldg(vals + begin + q) : 0.f;
+      };
+      int ci_cur, ci_nxt = -1;
+      float rv_cur, rv_nxt = 0.f;
+      fetch_idx(0, ci_cur, rv_cur);
+      if (nc > 1) fetch_idx(1, ci_nxt, rv_nxt);
+      auto produce = [&](int c) {
+        const uint32_t gi = g + c, s = gi % k8Stages, u = gi / k8Stages;
+        if (u > 0) umma::mbar_wait(&mbar_free[s], (u - 1) & 1);
+        uint8_t* st = base + s * k8StageBytes;
+#pragma unroll
+        for (int i = 0; i < KC / 2; ++i) {
+          const int t = t_sub + 2 * i;
+          const int ci = __shfl_sync(0xffffffffu, ci_cur, t);
+          cp_async16(st + blk_off + t * 128 + ((chunk ^ (t & 7)) << 4),
+                     reinterpret_cast<const uint8_t*>(src_hl) + (size_t)(ci < 0 ? 0 : ci) * (4 * K) + piece * 16, ci >= 0);
+        }
+        if (warp == 0) {   // rating columns: element 0 = bf16(r), element 1 = bf16(r - bf16(r))
+          const __nv_bfloat16 rh = __float2bfloat16_rn(rv_cur);
+          const __nv_bfloat16 rl = __float2bfloat16_rn(rv_cur - __bfloat162float(rh));
+          const uint32_t packed = (uint32_t)__bfloat16_as_ushort(rh) | ((uint32_t)__bfloat16_as_ushort(rl) << 16);
+          *reinterpret_cast<uint4*>(st + 4 * k8Blk + lane * 128 + ((0 ^ (lane & 7)) << 4)) = make_uint4(packed, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(st + 4 * k8Blk + lane * 128 + ((1 ^ (lane & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        cp_async_commit();
+        ci_cur = ci_nxt; rv_cur = rv_nxt;
+        if (c + 2 < nc) fetch_idx(c + 2, ci_nxt, rv_nxt);
+      };
+      for (int c = 0; c < k8Ahead; ++c) {
+        if (c < nc) produce(c); else cp_async_commit();
+      }
+      for (int c = 0; c < nc; ++c) {
+        if (c + k8Ahead < nc) produce(c + k8Ahead); else cp_async_commit();
+        cp_async_wait<k8Ahead>();
+        umma::fence_proxy_async();
+        bar_sync_n(1, 64);
+        if (tid == 0) {
+          if (c == 0 && it > 0) umma::mbar_wait(&mbar_tmem_free, (it - 1) & 1);   // previous accumulator drained
+          umma::fence_after_sync();
+          const uint32_t s = (g + c) % k8Stages;
+          const uint32_t sa = sbase + s * k8StageBytes;
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint64_t dH = umma::make_smem_desc(sa + ks * 2048, k8Blk, 1024, umma::kSwizzle128B);
+            const uint64_t dL = umma::make_smem_desc(sa + 2 * k8Blk + ks * 2048, k8Blk, 1024, umma::kSwizzle128B);
+            const uint64_t dR = umma::make_smem_desc(sa + 4 * k8Blk + ks * 2048, k8Blk, 1024, umma::kSwizzle128B);
+            const bool accum = (c | ks) != 0;
+            umma::mma_bf16(tmem, dH, dH, idesc256, accum);          // H^T [H | L]: the B descriptor walks H0 H1 L0 L1
+            umma::mma_bf16(tmem + 256, dH, dR, idesc16, accum);     // H^T R
+            umma::mma_bf16(tmem + 272, dL, dR, idesc16, accum);     // L^T R
+          }
+          umma::commit(&mbar_free[s]);
+          if (c == nc - 1) umma::commit(&mbar_acc[it & 1]);
+        }
+      }
+      g += nc;
+    }
+  } else {
+    // ================================================================ solver groups
+    float* HL = reinterpret_cast<float*>(base + k8Stages * k8StageBytes + group * k8GroupBytes);
+    const uint32_t P = umma::smem_u32(HL + 128 * k8LDH);
+    const uint32_t X = P + 2 * k8LDP * 4;
+    const int bar_base = 2 + 6 * group;                  // named barriers 2..7 (group A) / 8..13 (group B): 3 phase + 3 hand-shake
+    const uint32_t ta = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    uint32_t it = 0, mine = 0;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      if ((int)(it & 1) != group) continue;
+      const int row = item_row[item];
+      const int len = item_len[item];
+      const int slot = item_slot[item];
+      umma::mbar_wait(&mbar_acc[group], mine & 1);
+      ++mine;
+      umma::fence_after_sync();
+      // h l^T block -> shared (row m), so that its transpose can be read back
+      float e1[16], e2[16];
+      {
+        float v[32];
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          umma::tmem_ld32(ta + 128 + c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) HL[m * k8LDH + c0 + i] = v[i];
+        }
+        umma::tmem_ld16(ta + 256, e1);
+        umma::tmem_ld16(ta + 272, e2);
+      }
+      bar_sync_n(bar_base, 128);
+      const float lam = slot >= 0 ? 0.f : reg * (float)len;
+      f32x2 ap[64];
+      {
+        float v[32];
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          umma::tmem_ld32(ta + c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int n = c0 + i;
+            const float a0 = v[i] + HL[m * k8LDH + n] + HL[n * k8LDH + m] + (n == m ? lam : 0.f);
+            const float a1 = v[i + 1] + HL[m * k8LDH + n + 1] + HL[(n + 1) * k8LDH + m] + (n + 1 == m ? lam : 0.f);
+            ap[n / 2] = pack2(a0, a1);
+          }
+        }
+      }
+      const float bm = e1[0] + e1[1] + e2[0];
+      umma::fence_before_sync();
+      bar_sync_n(bar_base, 128);                          // every TMEM / HL read of this item is done
+      if (m == 0) umma::mbar_arrive(&mbar_tmem_free);
+      if (slot >= 0) {
+        float* W = workspace + (size_t)slot * k8SlotFloats;
+#pragma unroll
+        for (int n = 0; n < 128; n += 4)
+          *reinterpret_cast<float4*>(W + m * K + n) =
+              make_float4(lo2(ap[n / 2]), hi2(ap[n / 2]), lo2(ap[n / 2 + 1]), hi2(ap[n / 2 + 1]));
+        W[K * K + m] = bm;
+        if (m == 0) W[K * K + K] = (float)len;
+      } else {
+        const float x = ldlt128_rows(ap, bm, P, X, m, bar_base);
+        dst[(int64_t)row * K + m] = x;
+        bar_sync_n(bar_base, 128);                        // pivot slots / x hand-over are reused by the next item
+      }
+    }
+  }
+
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+// Long rows (rank 128): slot sums (pre-summed per group of 16 by als_slot_group_sum_kernel) + ridge + solve.
+__global__ void __launch_bounds__(128)
+als_reduce_solve128_kernel(const float* __restrict__ workspace, float* __restrict__ dst, float reg,
+                           const int32_t* __restrict__ long_row, const int32_t* __restrict__ long_slot0,
+                           const int32_t* __restrict__ long_nseg, int slot_group) {
+  constexpr int K = k8K;
+  __shared__ __align__(16) float PS[2 * k8LDP + 128];
+  const int m = threadIdx.x;
+  const int row = long_row[blockIdx.x];
+  const int s0 = long_slot0[blockIdx.x], ns = long_nseg[blockIdx.x];
+  float a[128];
+#pragma unroll
+  for (int n = 0; n < 128; ++n) a[n] = 0.f;
+  float bm = 0.f, cnt = 0.f;
+  const int stride = ns > slot_group ? slot_group : 1;
+  for (int q = 0; q < ns; q += stride) {
+    const float* W = workspace + (size_t)(s0 + q) * k8SlotFloats;
+#pragma unroll
+    for (int n = 0; n < 128; n += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(W + m * K + n);
+      a[n] += v.x; a[n + 1] += v.y; a[n + 2] += v.z; a[n + 3] += v.w;
+    }
+    bm += W[K * K + m];
+    cnt += W[K * K + K];
+  }
+  const float lam = reg * cnt;
+  f32x2 ap[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i)
+    ap[i] = pack2(a[2 * i] + (2 * i == m ? lam : 0.f), a[2 * i + 1] + (2 * i + 1 == m ? lam : 0.f));
+  const uint32_t P = umma::smem_u32(PS);
+  const float x = ldlt128_rows(ap, bm, P, P + 2 * k8LDP * 4, m, 1);
+  dst[(int64_t)row * K + m] = x;
+}
+
+int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_floats, cudaStream_t st);   // als_tc.cu
+int als_launch_split_bf16(const float* src, int64_t n_src, int k, void* out, cudaStream_t st);                 // als_tc.cu
+
+int als_half_step_tc128(const int32_t* colidx, const float* vals, const float* src, int64_t n_src, float* dst,
+                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st) {
+  __nv_bfloat16* hl = reinterpret_cast<__nv_bfloat16*>(split_buf);
+  if (int rc = als_launch_split_bf16(src, n_src, k8K, split_buf, st)) return rc;
+  const size_t smem = (size_t)k8Stages * k8StageBytes + 2 * (size_t)k8GroupBytes + 1024;
+  HALS_CUDA(cudaFuncSetAttribute(als_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = sm_count();
+  if (grid > plan->n_items) grid = plan->n_items;
+  als_tc128_kernel<<<(unsigned)grid, k8Threads, smem, st>>>(colidx, vals, hl, dst, reg, plan->item_row, plan->item_begin,
+                                                             plan->item_len, plan->item_slot, plan->n_items, slots);
+  HALS_LAUNCH_CHECK();
+  if (plan->n_long_rows > 0) {
+    constexpr int kGroup = 16;                            // == kSlotGroup of als_tc.cu
+    if (int rc = als_launch_slot_group_sum(slots, plan, (int)k8SlotFloats, st)) return rc;
+    als_reduce_solve128_kernel<<<(unsigned)plan->n_long_rows, 128, 0, st>>>(slots, dst, reg, plan->long_row,
+                                                                            plan->long_slot0, plan->long_nseg, kGroup);
+    HALS_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace hals

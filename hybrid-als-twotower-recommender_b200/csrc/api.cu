@@ -11,6 +11,8 @@ std::atomic<int64_t> g_launch_count{0};
 int als_half_step_simt(const int32_t* colidx, const float* vals, const float* src, float* dst, int k,
                        float reg, int implicit, float alpha, const float* gram,
                        const hals_als_plan* plan, float* ws, cudaStream_t st);
+int als_half_step_tc128(const int32_t* colidx, const float* vals, const float* src, int64_t n_src, float* dst,
+                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
 int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* src, int64_t n_src, float* dst,
                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
 }  // namespace hals
@@ -33,7 +35,7 @@ static size_t slot_region_bytes(int64_t n_slots, int k) {
 // tensor-core path: explicit feedback, rank 64 (HALS_FORCE_SIMT=1 routes everything to the SIMT path)
 static bool use_tc(int k, int implicit) {
   static const bool force_simt = [] { const char* e = getenv("HALS_FORCE_SIMT"); return e && e[0] == '1'; }();
-  return !force_simt && !implicit && k == 64;
+  return !force_simt && !implicit && (k == 64 || k == 128);
 }
 
 extern "C" size_t hals_als_workspace_bytes(int64_t n_slots, int k, int64_t n_src) {
@@ -130,6 +132,7 @@ extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, 
   HALS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
   if (use_tc(k, implicit)) {
     void* split = reinterpret_cast<uint8_t*>(workspace) + slot_region_bytes(plan->n_slots, k);
+    if (k == 128) return als_half_step_tc128(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
     return als_half_step_tc64(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
   }
   return als_half_step_simt(colidx, vals, src, dst, k, reg, implicit, alpha, gram, plan, (float*)workspace, st);
