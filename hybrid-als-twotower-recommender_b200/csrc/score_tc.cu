@@ -377,6 +377,22 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
       if (lane == 0) tma::arrive(&tmem_empty[buf]);
     }
 
+    if (PASS == 2) {
+      // trim every stream to its best `keep` before the exact re-scoring (fewer candidates to re-score; the
+      // verification bound then uses the keep-th bf16 score of the stream)
+      unsigned need = __ballot_sync(0xffffffffu, live && cnt > A.keep);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int64_t urow = u0 + q * 32 + src;
+        uint64_t* b = cand + ((size_t)vs * A.n_users + urow) * CAP;
+        const int c_src = __shfl_sync(0xffffffffu, cnt, src);
+        float t_new;
+        __syncwarp();
+        const int c_new = compact_row<CAP>(b, c_src, A.keep, lane, &t_new);
+        if (lane == src) { cnt = c_new; thr = t_new; }
+      }
+    }
     if (live) {
       if (PASS == 1) {
         const size_t o = (((size_t)vs * A.n_users + u) * 4) * kStExC;
@@ -453,12 +469,13 @@ __global__ void score_exact_extrema_kernel(ExactArgs E, const float* __restrict_
 // Pass 2: candidates (bf16 score keys) -> exact blend keys, in place.  One thread per candidate slot.
 __global__ void score_exact_blend_kernel(ExactArgs E, const float* __restrict__ extrema, float w_als, float w_tt,
                                          int32_t item_offset, uint64_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
-                                         int cap) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = gid / cap;                       // (split, user) row
-  const int e = (int)(gid - row * cap);
+                                         int cap, int sortn) {
+  const int64_t tidg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = tidg / sortn;                    // (stream, user) row; streams were trimmed to <= sortn keys
+  const int e = (int)(tidg - row * sortn);
   if (row >= (int64_t)E.n_splits * E.n_users) return;
   if (e >= cand_cnt[row]) return;
+  const int64_t gid = row * cap + e;
   const int64_t u = row % E.n_users;
   const int i = topk_key_index(cand[gid]);
   const float4 ex = reinterpret_cast<const float4*>(extrema)[u];
@@ -471,8 +488,8 @@ __global__ void score_exact_blend_kernel(ExactArgs E, const float* __restrict__ 
 }
 
 // Pass 2 finish: one warp per (split,user): sort the exact keys, write the top-k list, verify.
-template <int CAP>
-__global__ void score_select_kernel(uint64_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+template <int CAP /* keys sorted per stream (>= trimmed count) */>
+__global__ void score_select_kernel(int stride /* key slots per stream */, uint64_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
                                     const float* __restrict__ cand_thr, const float* __restrict__ extrema,
                                     const float2* __restrict__ unorm_scaled, const unsigned int* __restrict__ inorm_bits,
                                     float w_als, float w_tt, int64_t n_users, int n_splits, int topk,
@@ -481,9 +498,10 @@ __global__ void score_select_kernel(uint64_t* __restrict__ cand, const int32_t* 
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (int64_t)n_splits * n_users) return;
   const int64_t u = row % n_users;
-  uint64_t* buf = cand + (size_t)row * CAP;
+  uint64_t* buf = cand + (size_t)row * stride;
   uint64_t tkey;
-  const int c = topk_compact<CAP>(buf, cand_cnt[row], topk, lane, &tkey);
+  const int have = cand_cnt[row] < CAP ? cand_cnt[row] : CAP;   // surplus keys (score ties at the trim threshold) count as rejected
+  const int c = topk_compact<CAP>(buf, have, topk, lane, &tkey);
   int32_t* oi = out_idx + (size_t)row * topk;
   float* os = out_score + (size_t)row * topk;
   for (int e = lane; e < topk; e += 32) {
@@ -571,6 +589,21 @@ TcPlan make_plan(int64_t n_users, int64_t n_items, int ka, int kt, int topk) {
   const int64_t user_tiles = (n_users + kStM - 1) / kStM;
   const int64_t item_tiles = (n_items + kTcBN - 1) / kTcBN;
   int64_t splits = user_tiles > 0 ? (sm_count() + user_tiles - 1) / user_tiles : 1;
+  {
+    // one CTA per SM: pick the smallest multiple of the minimum split count whose CTA count fills whole waves
+    // (512 user tiles on 148 SMs: 1 split = 3.46 waves -> 4, 2 splits = 6.92 -> 7)
+    // The top-k pass pays for every extra candidate stream (more survivors to append and re-score), so it
+    // only splits further when a wave would otherwise be mostly empty; the extrema pass splits freely.
+    const int64_t base = splits;
+    const double good_enough = topk > 0 ? 0.80 : 0.95;
+    double best_eff = 0.0;
+    for (int64_t mult = 1; mult <= 4; ++mult) {
+      const double waves = (double)(user_tiles * base * mult) / sm_count();
+      const double eff = waves / (double)(int64_t)(waves + 0.999999);
+      if (eff > best_eff + 0.03) { best_eff = eff; splits = base * mult; }
+      if (best_eff >= good_enough) break;
+    }
+  }
   if (splits > item_tiles) splits = item_tiles;
   if (splits > 64) splits = 64;
   if (splits < 1) splits = 1;
@@ -722,15 +755,19 @@ extern "C" int hals_score_blend_topk(const float* Ua, int64_t ua_stride, const f
   if (rc) return rc;
   const int vsplits = 2 * p.splits;
   ExactArgs E{Ua, ua_stride, Ia, ia_stride, ka, Ut, ut_stride, It, it_stride, kt, n_users, vsplits};
-  const int64_t slots = (int64_t)vsplits * n_users * p.cap;
-  score_exact_blend_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(E, extrema, w_als, w_tt, item_offset, cand, cnt, p.cap);
+  int sortn = 64;
+  while (sortn < p.keep) sortn <<= 1;                   // streams leave the tensor-core kernel trimmed to `keep` keys
+  if (sortn < topk) sortn = p.cap;
+  const int64_t slots = (int64_t)vsplits * n_users * sortn;
+  score_exact_blend_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(E, extrema, w_als, w_tt, item_offset, cand, cnt, p.cap, sortn);
   HALS_LAUNCH_CHECK();
   int32_t* oi = (int32_t*)(W + p.off_pidx);
   float* os = (float*)(W + p.off_pscore);
   const unsigned sel_blocks = (unsigned)(((int64_t)vsplits * n_users + 3) / 4);
-  if (p.cap == 128) score_select_kernel<128><<<sel_blocks, 128, 0, st>>>(cand, cnt, thr, extrema, unorm, inorm, w_als, w_tt, n_users, vsplits, topk, oi, os, flag);
-  else if (p.cap == 256) score_select_kernel<256><<<sel_blocks, 128, 0, st>>>(cand, cnt, thr, extrema, unorm, inorm, w_als, w_tt, n_users, vsplits, topk, oi, os, flag);
-  else score_select_kernel<512><<<sel_blocks, 128, 0, st>>>(cand, cnt, thr, extrema, unorm, inorm, w_als, w_tt, n_users, vsplits, topk, oi, os, flag);
+  if (sortn == 64) score_select_kernel<64><<<sel_blocks, 128, 0, st>>>(p.cap, cand, cnt, thr, extrema, unorm, inorm, w_als, w_tt, n_users, vsplits, topk, oi, os, flag);
+  else if (sortn == 128) score_select_kernel<128><<<sel_blocks, 128, 0, st>>>(p.cap, cand, cnt, thr, extrema, unorm, inorm, w_als, w_tt, n_users, vsplits, topk, oi, os, flag);
+  else if (sortn == 256) score_select_kernel<256><<<sel_blocks, 128, 0, st>>>(p.cap, cand, cnt, thr, extrema, unorm, inorm, w_als, w_tt, n_users, vsplits, topk, oi, os, flag);
+  else score_select_kernel<512><<<sel_blocks, 128, 0, st>>>(p.cap, cand, cnt, thr, extrema, unorm, inorm, w_als, w_tt, n_users, vsplits, topk, oi, os, flag);
   HALS_LAUNCH_CHECK();
   if (int rc2 = hals_topk_merge(oi, os, vsplits, n_users, topk, out_idx, out_score, stream)) return rc2;
   score_verify_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(thr, extrema, unorm, inorm, w_als, w_tt, n_users,
