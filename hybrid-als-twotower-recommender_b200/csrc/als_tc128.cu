@@ -19,6 +19,8 @@
 // count shrinks as warps run out of rows (128 / 96 / 64 threads, then __syncwarp).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "als_common.cuh"
 #include "als_tc_common.cuh"
 #include "umma.cuh"
@@ -140,39 +142,17 @@ __device__ __forceinline__ float ldlt128_rows(f32x2 (&ap)[64], float rhs, uint32
   return x;
 }
 
-__global__ void __launch_bounds__(k8Threads, 1)
-als_tc128_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ vals,
-                 const __nv_bfloat16* __restrict__ src_hl, float* __restrict__ dst, float reg,
-                 const int32_t* __restrict__ item_row, const int64_t* __restrict__ item_begin,
-                 const int32_t* __restrict__ item_len, const int32_t* __restrict__ item_slot,
-                 int64_t n_items, float* __restrict__ workspace) {
+// Producer warps (0 and 1) of both rank-128 kernels: gather the h|l rows of every work item into the stage ring
+// and issue the three MMAs per 16 ratings; `mbar_acc[it & 1]` signals "accumulator of item it complete",
+// `mbar_tmem_free` is awaited before the first MMA of the next item.
+__device__ __forceinline__ void als128_producer(uint8_t* base, uint32_t sbase, uint32_t tmem, uint64_t* mbar_free,
+                                                uint64_t* mbar_acc, uint64_t* mbar_tmem_free,
+                                                const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                                const __nv_bfloat16* __restrict__ src_hl,
+                                                const int64_t* __restrict__ item_begin, const int32_t* __restrict__ item_len,
+                                                int64_t n_items) {
   constexpr int K = k8K, KC = k8KC;
-  extern __shared__ uint8_t smem_dyn[];
-  __shared__ uint64_t mbar_free[k8Stages];
-  __shared__ uint64_t mbar_acc[2];        // accumulator complete, one per solver group
-  __shared__ uint64_t mbar_tmem_free;     // accumulator drained
-  __shared__ uint32_t tmem_slot;
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool producer = warp < 2;
-  const int group = producer ? -1 : (warp - 2) >> 2;
-  const int m = 32 * (warp & 3) + lane;                 // solver: matrix row == TMEM lane
-  if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) {
-    for (int s = 0; s < k8Stages; ++s) umma::mbar_init(&mbar_free[s], 1);
-    umma::mbar_init(&mbar_acc[0], 1);
-    umma::mbar_init(&mbar_acc[1], 1);
-    umma::mbar_init(&mbar_tmem_free, 1);
-    umma::mbar_fence_init();
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  umma::fence_after_sync();
-  const uint32_t tmem = tmem_slot;
-  const uint32_t sbase = umma::smem_u32(base);
-
-  if (producer) {
     // ================================================================ producers
     constexpr uint32_t idesc256 = umma::make_instr_desc(umma::kFmtBF16, true, true, 128, 256);
     constexpr uint32_t idesc16 = umma::make_instr_desc(umma::kFmtBF16, true, true, 128, 16);
@@ -224,7 +204,7 @@ als_tc128_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ v
         umma::fence_proxy_async();
         bar_sync_n(1, 64);
         if (tid == 0) {
-          if (c == 0 && it > 0) umma::mbar_wait(&mbar_tmem_free, (it - 1) & 1);   // previous accumulator drained
+          if (c == 0 && it > 0) umma::mbar_wait(mbar_tmem_free, (it - 1) & 1);   // previous accumulator drained
           umma::fence_after_sync();
           const uint32_t s = (g + c) % k8Stages;
           const uint32_t sa = sbase + s * k8StageBytes;
@@ -244,6 +224,42 @@ als_tc128_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ v
       }
       g += nc;
     }
+}
+
+__global__ void __launch_bounds__(k8Threads, 1)
+als_tc128_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                 const __nv_bfloat16* __restrict__ src_hl, float* __restrict__ dst, float reg,
+                 const int32_t* __restrict__ item_row, const int64_t* __restrict__ item_begin,
+                 const int32_t* __restrict__ item_len, const int32_t* __restrict__ item_slot,
+                 int64_t n_items, float* __restrict__ workspace) {
+  constexpr int K = k8K, KC = k8KC;
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ uint64_t mbar_free[k8Stages];
+  __shared__ uint64_t mbar_acc[2];        // accumulator complete, one per solver group
+  __shared__ uint64_t mbar_tmem_free;     // accumulator drained
+  __shared__ uint32_t tmem_slot;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp < 2;
+  const int group = producer ? -1 : (warp - 2) >> 2;
+  const int m = 32 * (warp & 3) + lane;                 // solver: matrix row == TMEM lane
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int s = 0; s < k8Stages; ++s) umma::mbar_init(&mbar_free[s], 1);
+    umma::mbar_init(&mbar_acc[0], 1);
+    umma::mbar_init(&mbar_acc[1], 1);
+    umma::mbar_init(&mbar_tmem_free, 1);
+    umma::mbar_fence_init();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sbase = umma::smem_u32(base);
+
+  if (producer) {
+    als128_producer(base, sbase, tmem, mbar_free, mbar_acc, &mbar_tmem_free, colidx, vals, src_hl, item_begin, item_len, n_items);
   } else {
     // ================================================================ solver groups
     float* HL = reinterpret_cast<float*>(base + k8Stages * k8StageBytes + group * k8GroupBytes);
@@ -357,10 +373,12 @@ int als_half_step_tc128(const int32_t* colidx, const float* vals, const float* s
                         float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st) {
   __nv_bfloat16* hl = reinterpret_cast<__nv_bfloat16*>(split_buf);
   if (int rc = als_launch_split_bf16(src, n_src, k8K, split_buf, st)) return rc;
-  const size_t smem = (size_t)k8Stages * k8StageBytes + 2 * (size_t)k8GroupBytes + 1024;
-  HALS_CUDA(cudaFuncSetAttribute(als_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (a two-threads-per-row variant of the solver was measured slower: 208 vs 129 ms / sweep on c3 -- the
+  //  256-thread step barrier and the extra column exchange cost more than the shorter per-thread stream saves)
   int64_t grid = sm_count();
   if (grid > plan->n_items) grid = plan->n_items;
+  const size_t smem = (size_t)k8Stages * k8StageBytes + 2 * (size_t)k8GroupBytes + 1024;
+  HALS_CUDA(cudaFuncSetAttribute(als_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   als_tc128_kernel<<<(unsigned)grid, k8Threads, smem, st>>>(colidx, vals, hl, dst, reg, plan->item_row, plan->item_begin,
                                                              plan->item_len, plan->item_slot, plan->n_items, slots);
   HALS_LAUNCH_CHECK();
