@@ -466,25 +466,49 @@ __global__ void score_exact_extrema_kernel(ExactArgs E, const float* __restrict_
   if (any && !(best >= bound + eps) && bound > ninf) atomicOr(flag + u, 1);
 }
 
-// Pass 2: candidates (bf16 score keys) -> exact blend keys, in place.  One thread per candidate slot.
+// Pass 2: candidates (bf16 score keys) -> exact fp32 blend keys, in place.  One warp per candidate stream
+// (stream, user): the user's two vectors stay in registers, every candidate's item rows are read with
+// coalesced 128-byte warp loads and reduced with shuffles (fp32; the summation order differs from the
+// CUDA-core path's sequential fmaf only in the last bits).
 __global__ void score_exact_blend_kernel(ExactArgs E, const float* __restrict__ extrema, float w_als, float w_tt,
                                          int32_t item_offset, uint64_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
                                          int cap, int sortn) {
-  const int64_t tidg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = tidg / sortn;                    // (stream, user) row; streams were trimmed to <= sortn keys
-  const int e = (int)(tidg - row * sortn);
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (stream, user)
   if (row >= (int64_t)E.n_splits * E.n_users) return;
-  if (e >= cand_cnt[row]) return;
-  const int64_t gid = row * cap + e;
+  int n = cand_cnt[row];
+  if (n > sortn) n = sortn;
+  if (n <= 0) return;
   const int64_t u = row % E.n_users;
-  const int i = topk_key_index(cand[gid]);
+  float ua[4], ut[2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) ua[q] = (lane + 32 * q < E.ka) ? E.Ua[u * E.ua_stride + lane + 32 * q] : 0.f;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) ut[q] = (lane + 32 * q < E.kt) ? E.Ut[u * E.ut_stride + lane + 32 * q] : 0.f;
   const float4 ex = reinterpret_cast<const float4*>(extrema)[u];
   const float ra = ex.y - ex.x, rt = ex.w - ex.z;
   const float sca = (ra != 0.f) ? 1.f / ra : 1.f, sct = (rt != 0.f) ? 1.f / rt : 1.f;
-  const float sa = E.ka ? dot_seq(E.Ua + u * E.ua_stride, E.Ia + (int64_t)i * E.ia_stride, E.ka) : 0.f;
-  const float st = E.kt ? dot_seq(E.Ut + u * E.ut_stride, E.It + (int64_t)i * E.it_stride, E.kt) : 0.f;
-  const float b = fmaf(w_als, (sa - ex.x) * sca, w_tt * ((st - ex.z) * sct));   // == blend_value() of the SIMT path
-  cand[gid] = topk_key(b, i + item_offset);
+  uint64_t* buf = cand + (size_t)row * cap;
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const uint64_t mykey = (e0 + lane < n) ? buf[e0 + lane] : 0ull;
+    const int cnt = min(32, n - e0);
+    uint64_t outkey = 0ull;
+    for (int e = 0; e < cnt; ++e) {
+      const int i = topk_key_index(__shfl_sync(0xffffffffu, mykey, e));
+      const float* ia = E.Ia + (int64_t)i * E.ia_stride;
+      const float* it = E.It + (int64_t)i * E.it_stride;
+      float sa = 0.f, st = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (lane + 32 * q < E.ka) sa = fmaf(ua[q], ia[lane + 32 * q], sa);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) if (lane + 32 * q < E.kt) st = fmaf(ut[q], it[lane + 32 * q], st);
+      sa = warp_sum(sa);
+      st = warp_sum(st);
+      const float b = fmaf(w_als, (sa - ex.x) * sca, w_tt * ((st - ex.z) * sct));   // == blend_value()
+      if (lane == e) outkey = topk_key(b, i + item_offset);
+    }
+    if (e0 + lane < n) buf[e0 + lane] = outkey;
+  }
 }
 
 // Pass 2 finish: one warp per (split,user): sort the exact keys, write the top-k list, verify.
@@ -759,7 +783,8 @@ extern "C" int hals_score_blend_topk(const float* Ua, int64_t ua_stride, const f
   while (sortn < p.keep) sortn <<= 1;                   // streams leave the tensor-core kernel trimmed to `keep` keys
   if (sortn < topk) sortn = p.cap;
   const int64_t slots = (int64_t)vsplits * n_users * sortn;
-  score_exact_blend_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(E, extrema, w_als, w_tt, item_offset, cand, cnt, p.cap, sortn);
+  (void)slots;
+  score_exact_blend_kernel<<<(unsigned)(((int64_t)vsplits * n_users + 7) / 8), 256, 0, st>>>(E, extrema, w_als, w_tt, item_offset, cand, cnt, p.cap, sortn);
   HALS_LAUNCH_CHECK();
   int32_t* oi = (int32_t*)(W + p.off_pidx);
   float* os = (float*)(W + p.off_pscore);
