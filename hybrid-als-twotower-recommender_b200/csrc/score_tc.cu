@@ -86,8 +86,9 @@ __global__ void score_prep_kernel(const float* __restrict__ A, int64_t a_stride,
   if (lane == 0) {
     if (norm_out) norm_out[row] = make_float2(na, nt);
     if (max_norm_bits) {
-      atomicMax(max_norm_bits + 0, __float_as_uint(na));
-      atomicMax(max_norm_bits + 1, __float_as_uint(nt));
+      // racy pre-check keeps 1.25M rows from serialising on two addresses; the atomic decides
+      if (__float_as_uint(na) > *(volatile unsigned int*)(max_norm_bits + 0)) atomicMax(max_norm_bits + 0, __float_as_uint(na));
+      if (__float_as_uint(nt) > *(volatile unsigned int*)(max_norm_bits + 1)) atomicMax(max_norm_bits + 1, __float_as_uint(nt));
     }
   }
 }
@@ -435,7 +436,8 @@ struct ExactArgs {
 __global__ void score_exact_extrema_kernel(ExactArgs E, const float* __restrict__ ex_val, const int32_t* __restrict__ ex_idx,
                                            const float2* __restrict__ unorm, const unsigned int* __restrict__ inorm_bits,
                                            float* __restrict__ extrema, int32_t* __restrict__ flag) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t gid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per (user, list)
   const int64_t u = gid >> 2;
   const int l = (int)(gid & 3);                        // 0 max_a, 1 min_a, 2 max_t, 3 min_t
   if (u >= E.n_users) return;
@@ -443,6 +445,11 @@ __global__ void score_exact_extrema_kernel(ExactArgs E, const float* __restrict_
   const float ninf = -__int_as_float(0x7f800000);
   const float* uv = is_t ? E.Ut + u * E.ut_stride : E.Ua + u * E.ua_stride;
   const int k = is_t ? E.kt : E.ka;
+  const int64_t istride = is_t ? E.it_stride : E.ia_stride;
+  const float* ibase = is_t ? E.It : E.Ia;
+  float uq[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) uq[q] = (lane + 32 * q < k) ? uv[lane + 32 * q] : 0.f;
   float best = ninf, bound = ninf;
   bool any = false;
   for (int s = 0; s < E.n_splits; ++s) {
@@ -450,14 +457,18 @@ __global__ void score_exact_extrema_kernel(ExactArgs E, const float* __restrict_
     for (int p = 0; p < kStExC; ++p) {
       const int i = ex_idx[o + p];
       if (i < 0) continue;
-      const float* iv = is_t ? E.It + (int64_t)i * E.it_stride : E.Ia + (int64_t)i * E.ia_stride;
-      const float sc = dot_seq(uv, iv, k);
+      const float* iv = ibase + (int64_t)i * istride;
+      float sc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (lane + 32 * q < k) sc = fmaf(uq[q], iv[lane + 32 * q], sc);
+      sc = warp_sum(sc);
       best = fmaxf(best, is_min ? -sc : sc);
       any = true;
     }
     // everything this split rejected scored (in bf16) no better than its weakest kept candidate
     if (ex_idx[o + kStExC - 1] >= 0) bound = fmaxf(bound, ex_val[o + kStExC - 1]);
   }
+  if (lane != 0) return;
   const float2 un = unorm[u];
   const float eps = 1.05f * 0.00390625f * (is_t ? un.y * __uint_as_float(inorm_bits[1]) : un.x * __uint_as_float(inorm_bits[0]));
   if (k == 0) { best = 0.f; any = true; bound = ninf; }
@@ -723,7 +734,7 @@ extern "C" int hals_score_extrema(const float* Ua, int64_t ua_stride, const floa
   if (int rc = launch_tc<1, 128, 128>(mu, mi, A, p.nkb_a + p.nkb_t, (float*)(W + p.off_exv), (int32_t*)(W + p.off_exi),
                                       nullptr, nullptr, nullptr, st)) return rc;
   ExactArgs E{Ua, ua_stride, Ia, ia_stride, ka, Ut, ut_stride, It, it_stride, kt, n_users, 2 * p.splits};
-  score_exact_extrema_kernel<<<(unsigned)((n_users * 4 + 255) / 256), 256, 0, st>>>(
+  score_exact_extrema_kernel<<<(unsigned)((n_users * 4 + 7) / 8), 256, 0, st>>>(
       E, (const float*)(W + p.off_exv), (const int32_t*)(W + p.off_exi), unorm, inorm, extrema, flag);
   HALS_LAUNCH_CHECK();
   score_flag_list_kernel<<<(unsigned)((n_users + 255) / 256), 256, 0, st>>>(flag, n_users, 1, list, fcount, extrema);
