@@ -105,14 +105,6 @@ __device__ __forceinline__ void insert4(float (&v)[kStExC], int (&ix)[kStExC], f
   }
 }
 
-// v[c] for a run-time c without spilling the register array (rare path: one survivor)
-__device__ __forceinline__ float select32(const float (&v)[32], int c) {
-  float s = v[0];
-#pragma unroll
-  for (int i = 1; i < 32; ++i) s = (i == c) ? v[i] : s;
-  return s;
-}
-
 // Out of line on purpose: the hot epilogue loop must stay small enough for the instruction cache.
 template <int CAP>
 __device__ __noinline__ int compact_row(uint64_t* buf, int count, int keep, int lane, float* thr_out) {
@@ -125,8 +117,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
                 float* __restrict__ ex_val /* [splits][U][4][4] */, int32_t* __restrict__ ex_idx,
                 uint64_t* __restrict__ cand /* [splits][U][CAP] */, int32_t* __restrict__ cand_cnt,
                 float* __restrict__ cand_thr /* [splits][U] */) {
-  constexpr int NACC = (PASS == 1) ? 2 : 1;            // accumulators per buffer
-  constexpr int BUFCOLS = NACC * BN;                   // TMEM columns per buffer (256)
+  constexpr int JPT = (PASS == 1) ? 2 : 1;             // accumulator jobs per item tile: pass 1 scores the two models
+                                                       // one after the other (N = 256 each: an N = 128 MMA pair is
+                                                       // shared-memory-bandwidth bound at M = 128)
+  constexpr int BUFCOLS = BN;                          // TMEM columns per buffer (256), two buffers
   constexpr uint32_t kABlk = kStM * 128;               // bytes of one [128 x 64] bf16 block
   constexpr uint32_t kBBlk = BN * 128;
   extern __shared__ uint8_t smem_dyn[];
@@ -191,29 +185,32 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
       umma::mbar_wait(&a_full, 0);
       uint32_t g = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        const uint32_t buf = t & 1, use = t >> 1;
-        HALS_SPF(0);
-        if (use > 0) umma::mbar_wait(&tmem_empty[buf], (use - 1) & 1);
-        HALS_SPF(1);
-        umma::fence_after_sync();
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const uint32_t s = g % kStRing, u = g / kStRing;
-          HALS_SPF(0);
-          umma::mbar_wait(&full[s], u & 1);
-          HALS_SPF(2);
-          umma::fence_after_sync();
-          const bool t_part = kb >= A.nkb_a;
-          const uint32_t d = tmem + buf * BUFCOLS + ((PASS == 1 && t_part) ? BN : 0);
-          const bool first_kb = (PASS == 1) ? (kb == 0 || kb == A.nkb_a) : (kb == 0);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = umma::make_smem_desc(sA + kb * kABlk + ks * 32, 16, 1024, umma::kSwizzle128B);
-            const uint64_t bd = umma::make_smem_desc(sB + s * kBBlk + ks * 32, 16, 1024, umma::kSwizzle128B);
-            umma::mma_bf16(d, ad, bd, idesc, !(first_kb && ks == 0));
+        for (int m = 0; m < JPT; ++m) {
+          const uint32_t job = (uint32_t)t * JPT + m, buf = job & 1, use = job >> 1;
+          const int kb0 = (PASS == 1 && m == 1) ? A.nkb_a : 0;
+          const int kb1 = (PASS == 1 && m == 0) ? A.nkb_a : nkb;
+          HALS_SPF(0);
+          if (use > 0) umma::mbar_wait(&tmem_empty[buf], (use - 1) & 1);
+          HALS_SPF(1);
+          umma::fence_after_sync();
+          const uint32_t d = tmem + buf * BUFCOLS;
+          for (int kb = kb0; kb < kb1; ++kb, ++g) {
+            const uint32_t s = g % kStRing, u = g / kStRing;
+            HALS_SPF(0);
+            umma::mbar_wait(&full[s], u & 1);
+            HALS_SPF(2);
+            umma::fence_after_sync();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ad = umma::make_smem_desc(sA + kb * kABlk + ks * 32, 16, 1024, umma::kSwizzle128B);
+              const uint64_t bd = umma::make_smem_desc(sB + s * kBBlk + ks * 32, 16, 1024, umma::kSwizzle128B);
+              umma::mma_bf16(d, ad, bd, idesc, !(kb == kb0 && ks == 0));
+            }
+            umma::commit(&empty[s]);
           }
-          umma::commit(&empty[s]);
+          umma::commit(&tmem_full[buf]);                // a model without K blocks (rank 0) completes at once
         }
-        umma::commit(&tmem_full[buf]);
       }
     }
   } else {
@@ -246,58 +243,61 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
     }
 
     for (int t = 0; t < n_tiles; ++t) {
-      const uint32_t buf = t & 1, use = t >> 1;
+     const int64_t it0 = i_begin + (int64_t)t * BN;
+     const bool ragged = it0 + BN > i_end;              // only the last tile of a range
+#pragma unroll
+     for (int m = 0; m < JPT; ++m) {
+      const uint32_t job = (uint32_t)t * JPT + m, buf = job & 1, use = job >> 1;
       HALS_SPF(0);
       umma::mbar_wait(&tmem_full[buf], use & 1);
       HALS_SPF(1);
       umma::fence_after_sync();
-      const int64_t it0 = i_begin + (int64_t)t * BN;
-      const bool ragged = it0 + BN > i_end;             // only the last tile of a range
       // software pipeline over the 32-column groups of this warp's half: the tcgen05.ld of group g+1 is in
       // flight while group g is filtered
       const uint32_t tbase = tq + buf * BUFCOLS;
       constexpr int G = HB / 32;
       if (PASS == 1) {
-        float va[2][32], vt[2][32];
-        umma::tmem_ld32_issue(tbase + half * HB, va[0]);
-        umma::tmem_ld32_issue(tbase + BN + half * HB, vt[0]);
+        // job m holds model m's scores (0 = ALS, 1 = tower): lists 2m (maxima) and 2m+1 (minima, as -s)
+        const bool present = (m == 0) ? (A.nkb_a > 0) : (A.nkb_t > 0);
+        if (present) {
+          float vv[2][32];
+          umma::tmem_ld32_issue(tbase + half * HB, vv[0]);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int c0 = half * HB + g * 32;
-          umma::tmem_wait_ld_dep(va[g & 1]);
-          umma::tmem_wait_ld_dep(vt[g & 1]);
-          if (g + 1 < G) {
-            umma::tmem_ld32_issue(tbase + c0 + 32, va[(g + 1) & 1]);
-            umma::tmem_ld32_issue(tbase + BN + c0 + 32, vt[(g + 1) & 1]);
-          }
-          const float (&a32)[32] = va[g & 1];
-          const float (&t32)[32] = vt[g & 1];
-          // group extremes first (FMNMX3 chains); the per-column code runs only when one of the four
-          // candidate lists can actually change (about 0.5% of the groups per thread)
-          float mxa = a32[0], mna = a32[0], mxt = t32[0], mnt = t32[0];
+          for (int g = 0; g < G; ++g) {
+            const int c0 = half * HB + g * 32;
+            umma::tmem_wait_ld_dep(vv[g & 1]);
+            if (g + 1 < G) umma::tmem_ld32_issue(tbase + c0 + 32, vv[(g + 1) & 1]);
+            const float (&v)[32] = vv[g & 1];
+            // Extremes of each 8-column octet first (FMNMX3 chains).  A warp runs an octet's per-column code only
+            // when some lane can change one of its two lists there, and that code walks 8 columns, not 32.
+            const float t0 = xv[2 * m][kStExC - 1], t1 = xv[2 * m + 1][kStExC - 1];
+            float mx[4], mn[4];                         // all eight chains first: they overlap, the branches come after
 #pragma unroll
-          for (int c = 1; c < 32; ++c) {
-            mxa = fmaxf(mxa, a32[c]); mna = fminf(mna, a32[c]);
-            mxt = fmaxf(mxt, t32[c]); mnt = fminf(mnt, t32[c]);
-          }
-          if (live && (mxa > xv[0][kStExC - 1] || -mna > xv[1][kStExC - 1] || mxt > xv[2][kStExC - 1] || -mnt > xv[3][kStExC - 1])) {
-            // which columns can enter a list: branch-free bitmask, then visit only the set bits (usually one)
-            unsigned m = 0;
-            const float t0 = xv[0][kStExC - 1], t1 = xv[1][kStExC - 1], t2 = xv[2][kStExC - 1], t3 = xv[3][kStExC - 1];
+            for (int o = 0; o < 4; ++o) {
+              mx[o] = v[8 * o]; mn[o] = v[8 * o];
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              m |= ((a32[c] > t0 || -a32[c] > t1 || t32[c] > t2 || -t32[c] > t3) ? 1u : 0u) << c;
-            while (m) {
-              const int c = __ffs(m) - 1;
-              m &= m - 1;
-              const int64_t i = it0 + c0 + c;
-              if (!ragged || i < i_end) {
-                const float a = select32(a32, c), tt = select32(t32, c);
-                const int gi = (int)i;
-                insert4(xv[0], xi[0], a, gi);
-                insert4(xv[1], xi[1], -a, gi);
-                insert4(xv[2], xi[2], tt, gi);
-                insert4(xv[3], xi[3], -tt, gi);
+              for (int c = 1; c < 8; ++c) { mx[o] = fmaxf(mx[o], v[8 * o + c]); mn[o] = fminf(mn[o], v[8 * o + c]); }
+            }
+            const float gmx = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), gmn = fminf(fminf(mn[0], mn[1]), fminf(mn[2], mn[3]));
+            if (live && (gmx > t0 || -gmn > t1))
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              if (mx[o] > t0 || -mn[o] > t1) {
+                unsigned mk = 0;                         // thresholds may be stale within the octet: insert4 re-checks
+#pragma unroll
+                for (int c = 0; c < 8; ++c) mk |= ((v[8 * o + c] > t0 || -v[8 * o + c] > t1) ? 1u : 0u) << c;
+                while (mk) {
+                  const int c = __ffs(mk) - 1;
+                  mk &= mk - 1;
+                  const int64_t i = it0 + c0 + 8 * o + c;
+                  if (!ragged || i < i_end) {
+                    float s = v[8 * o];
+#pragma unroll
+                    for (int cc = 1; cc < 8; ++cc) s = (cc == c) ? v[8 * o + cc] : s;
+                    insert4(xv[2 * m], xi[2 * m], s, (int)i);
+                    insert4(xv[2 * m + 1], xi[2 * m + 1], -s, (int)i);
+                  }
+                }
               }
             }
           }
@@ -311,50 +311,39 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
           umma::tmem_wait_ld_dep(vv[g & 1]);
           if (g + 1 < G) umma::tmem_ld32_issue(tbase + c0 + 32, vv[(g + 1) & 1]);
           const float (&v)[32] = vv[g & 1];
-          // Common case: nothing in these 32 columns beats the row threshold -> one FMNMX3 chain and one
-          // compare.  Survivors are ~0.2% of the items, so a thread rarely has one and almost never two: the
-          // single survivor is located by a max tree + descent; only if the runner-up also beats the threshold
-          // does the full bitmask path run.
-          float gmax = v[0];
+          // Octet maxima (FMNMX3 chains) against the row threshold.  Survivors are ~0.4% of the items: most lanes
+          // have none in a group, but some lane of the warp nearly always has one, so what matters is how much
+          // code that lane drags the warp through -- an 8-column bitmask, and for the usual single survivor the
+          // octet maximum IS its score (no register selection).
+          float gm4[4];
 #pragma unroll
-          for (int c = 1; c < 32; ++c) gmax = fmaxf(gmax, v[c]);
-          if (gmax > thr) {
-            float l1[16], l2[8], l3[4];
+          for (int o = 0; o < 4; ++o) {
+            gm4[o] = v[8 * o];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) l1[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+            for (int c = 1; c < 8; ++c) gm4[o] = fmaxf(gm4[o], v[8 * o + c]);
+          }
+          if (fmaxf(fmaxf(gm4[0], gm4[1]), fmaxf(gm4[2], gm4[3])) > thr)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) l2[i] = fmaxf(l1[2 * i], l1[2 * i + 1]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) l3[i] = fmaxf(l2[2 * i], l2[2 * i + 1]);
-            const float l40 = fmaxf(l3[0], l3[1]), l41 = fmaxf(l3[2], l3[3]);
-            // descent (ties go left = lower column); `sib` collects the best value NOT on the path
-            int ix = l41 > l40;
-            float sib = ix ? l40 : l41;
-            { const float a = ix ? l3[2] : l3[0], b = ix ? l3[3] : l3[1]; const int r = b > a; sib = fmaxf(sib, r ? a : b); ix = ix * 2 + r; }
-            { float a = l2[0], b = l2[1];
-#pragma unroll
-              for (int i = 1; i < 4; ++i) { a = (ix == i) ? l2[2 * i] : a; b = (ix == i) ? l2[2 * i + 1] : b; }
-              const int r = b > a; sib = fmaxf(sib, r ? a : b); ix = ix * 2 + r; }
-            { float a = l1[0], b = l1[1];
-#pragma unroll
-              for (int i = 1; i < 8; ++i) { a = (ix == i) ? l1[2 * i] : a; b = (ix == i) ? l1[2 * i + 1] : b; }
-              const int r = b > a; sib = fmaxf(sib, r ? a : b); ix = ix * 2 + r; }
-            { float a = v[0], b = v[1];
-#pragma unroll
-              for (int i = 1; i < 16; ++i) { a = (ix == i) ? v[2 * i] : a; b = (ix == i) ? v[2 * i + 1] : b; }
-              const int r = b > a; sib = fmaxf(sib, r ? a : b); ix = ix * 2 + r; }
-            if (!(sib > thr)) {
-              const int64_t i = it0 + c0 + ix;
-              if (!ragged || i < i_end) mybuf[cnt++] = topk_key(gmax, (int32_t)i);
-            } else {
+          for (int o = 0; o < 4; ++o) {
+            const float gm = gm4[o];
+            if (gm > thr) {
               unsigned m = 0;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) m |= (v[c] > thr ? 1u : 0u) << c;
-              while (m) {
-                const int c = __ffs(m) - 1;
-                m &= m - 1;
-                const int64_t i = it0 + c0 + c;
-                if (!ragged || i < i_end) mybuf[cnt++] = topk_key(select32(v, c), (int32_t)i);
+              for (int c = 0; c < 8; ++c) m |= (v[8 * o + c] > thr ? 1u : 0u) << c;
+              const int64_t ib = it0 + c0 + 8 * o;
+              if ((m & (m - 1)) == 0) {
+                const int64_t i = ib + (__ffs(m) - 1);
+                if (!ragged || i < i_end) mybuf[cnt++] = topk_key(gm, (int32_t)i);
+              } else {
+                while (m) {
+                  const int c = __ffs(m) - 1;
+                  m &= m - 1;
+                  float s = v[8 * o];
+#pragma unroll
+                  for (int cc = 1; cc < 8; ++cc) s = (cc == c) ? v[8 * o + cc] : s;
+                  const int64_t i = ib + c;
+                  if (!ragged || i < i_end) mybuf[cnt++] = topk_key(s, (int32_t)i);
+                }
               }
             }
           }
@@ -376,6 +365,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
       umma::fence_before_sync();
       __syncwarp();
       if (lane == 0) tma::arrive(&tmem_empty[buf]);
+     }
     }
 
     if (PASS == 2) {
@@ -728,10 +718,10 @@ extern "C" int hals_score_extrema(const float* Ua, int64_t ua_stride, const floa
   HALS_LAUNCH_CHECK();
   CUtensorMap mu, mi;
   if (!tma::make_bf16_rowmajor_map(&mu, ub, (uint64_t)n_users, (uint64_t)p.Kp, kStM) ||
-      !tma::make_bf16_rowmajor_map(&mi, ib, (uint64_t)n_items, (uint64_t)p.Kp, 128))
+      !tma::make_bf16_rowmajor_map(&mi, ib, (uint64_t)n_items, (uint64_t)p.Kp, kTcBN))
     return fail(HALS_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", __func__);
   ScoreTcArgs A{p.nkb_a, p.nkb_t, n_users, n_items, p.items_per_split, p.splits, p.keep, 0};
-  if (int rc = launch_tc<1, 128, 128>(mu, mi, A, p.nkb_a + p.nkb_t, (float*)(W + p.off_exv), (int32_t*)(W + p.off_exi),
+  if (int rc = launch_tc<1, kTcBN, 128>(mu, mi, A, p.nkb_a + p.nkb_t, (float*)(W + p.off_exv), (int32_t*)(W + p.off_exi),
                                       nullptr, nullptr, nullptr, st)) return rc;
   ExactArgs E{Ua, ua_stride, Ia, ia_stride, ka, Ut, ut_stride, It, it_stride, kt, n_users, 2 * p.splits};
   score_exact_extrema_kernel<<<(unsigned)((n_users * 4 + 7) / 8), 256, 0, st>>>(
