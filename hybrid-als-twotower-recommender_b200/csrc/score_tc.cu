@@ -303,28 +303,40 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
           }
         }
       } else {
-        float vv[2][32];
-        umma::tmem_ld32_issue(tbase + half * HB, vv[0]);
+        // W columns per step (two tcgen05.ld x32 in flight per buffer when the candidate buffer leaves room for 64
+        // new keys): more independent FMNMX3 chains per wait, half as many waits, branches and ballots
+        constexpr int W = (CAP >= 256) ? 64 : 32;
+        constexpr int G2 = HB / W;
+        float vv[2][W];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int c0 = half * HB + g * 32;
-          umma::tmem_wait_ld_dep(vv[g & 1]);
-          if (g + 1 < G) umma::tmem_ld32_issue(tbase + c0 + 32, vv[(g + 1) & 1]);
-          const float (&v)[32] = vv[g & 1];
+        for (int x = 0; x < W / 32; ++x) umma::tmem_ld32_issue(tbase + half * HB + 32 * x, vv[0] + 32 * x);
+#pragma unroll
+        for (int g = 0; g < G2; ++g) {
+          const int c0 = half * HB + g * W;
+#pragma unroll
+          for (int x = 0; x < W / 32; ++x) umma::tmem_wait_ld_dep(vv[g & 1] + 32 * x);
+          if (g + 1 < G2) {
+#pragma unroll
+            for (int x = 0; x < W / 32; ++x) umma::tmem_ld32_issue(tbase + c0 + W + 32 * x, vv[(g + 1) & 1] + 32 * x);
+          }
+          const float (&v)[W] = vv[g & 1];
           // Octet maxima (FMNMX3 chains) against the row threshold.  Survivors are ~0.4% of the items: most lanes
           // have none in a group, but some lane of the warp nearly always has one, so what matters is how much
           // code that lane drags the warp through -- an 8-column bitmask, and for the usual single survivor the
           // octet maximum IS its score (no register selection).
-          float gm4[4];
+          float gm4[W / 8];
 #pragma unroll
-          for (int o = 0; o < 4; ++o) {
+          for (int o = 0; o < W / 8; ++o) {
             gm4[o] = v[8 * o];
 #pragma unroll
             for (int c = 1; c < 8; ++c) gm4[o] = fmaxf(gm4[o], v[8 * o + c]);
           }
-          if (fmaxf(fmaxf(gm4[0], gm4[1]), fmaxf(gm4[2], gm4[3])) > thr)
+          float gall = gm4[0];
 #pragma unroll
-          for (int o = 0; o < 4; ++o) {
+          for (int o = 1; o < W / 8; ++o) gall = fmaxf(gall, gm4[o]);
+          if (gall > thr)
+#pragma unroll
+          for (int o = 0; o < W / 8; ++o) {
             const float gm = gm4[o];
             if (gm > thr) {
               unsigned m = 0;
@@ -347,8 +359,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
               }
             }
           }
-          // compaction: a row may not enter the next 32 columns with fewer than 32 free slots
-          unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
+          // compaction: a row may not enter the next W columns with fewer than W free slots
+          unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - W);
           while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
