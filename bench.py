@@ -362,6 +362,14 @@ def main():
         return
     peak, peak_src = measured_peaks()
     b_item, b_user = algorithmic_bytes(w)
+    traffic = None          # measured DRAM bytes per sweep (both launches), from the committed ncu capture of this workload
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f).get(args.workload)
+        if tr and world == 1:
+            traffic = sum(tr[h][k] for h in ("item_half", "user_half") for k in ("dram_read_bytes", "dram_write_bytes"))
+    except (OSError, ValueError, KeyError):
+        traffic = None
     # per-rank share of the algorithmic bytes (rows are nnz-balanced across ranks)
     ach = (b_item + b_user) / world / ((t_item + t_user) * 1e-3) / 1e9
     line = {
@@ -377,7 +385,9 @@ def main():
                 "ms_per_call": float(te), "what": "pinned host COO -> H2D -> CSR build + plan -> sweeps -> factors D2H"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                     "traffic_note": "DRAM bytes per sweep (item + user launch) from profiles/r01_traffic.json (ncu --set full); "
+                                     "far below the algorithmic bytes because the gathered factor rows are served by the 126 MB L2",
                      "kernel": "als half-step (build normal equations + Cholesky solve), item + user launches",
                      "algorithmic_bytes_per_sweep": b_item + b_user, "ms_item_half": t_item, "ms_user_half": t_user,
                      "peak_source": peak_src},
