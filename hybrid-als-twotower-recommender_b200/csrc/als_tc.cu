@@ -31,7 +31,7 @@ namespace hals {
 constexpr int kTcThreads = 128;
 constexpr int kTcKC = 32;          // ratings per stage
 #ifndef HALS_TC_STAGES
-#define HALS_TC_STAGES 4
+#define HALS_TC_STAGES 3
 #endif
 #ifndef HALS_TC_AHEAD
 #define HALS_TC_AHEAD 2
@@ -43,7 +43,9 @@ constexpr int kTcRowBytes = 128;   // one 64-wide bf16 MN atom row
 constexpr int kTcBlk = kTcKC * kTcRowBytes;          // 4096: one [KC][64] block
 constexpr int kTcStageBytes = 3 * kTcBlk;            // H | L | R
 constexpr int kTcLD = kTcK + 1;
-constexpr int kTcLDP = 68;                            // published pivot rows: 16-byte aligned rows
+constexpr int kTcLDP = 68;                            // published pivot rows: 16-byte aligned rows (ldlt64_rows)
+constexpr int kTcLDS = 68;                            // accumulator hand-over rows: conflict-free 16-byte stores
+constexpr int kTcSolverBytes = 64 * 68 * 4 + 256 + 256 + 128;   // Pall (every published pivot column) + y, z, x rows
 constexpr int kTcS1Floats = 3 * kTcLDP;              // two pivot-row slots + the x hand-over row
 constexpr int kTcTmemCols = 128;
 constexpr int kTcN = 80;
@@ -203,6 +205,138 @@ __device__ __forceinline__ float ldlt64_rows(f32x2 (&ap)[32], float rhs, uint32_
   return x;
 }
 
+// ---- 2-D cyclic register tiling (the main kernel's solver) --------------------------------------------
+// With thread = matrix row every thread needs the WHOLE pivot row at every step (64 threads x 256 B per step)
+// and executes ~75 instructions per step for it.  Here solver thread s = 8*ti + tj owns the 8 x 8 sub-matrix
+// A[ti + 8r][tj + 8c] (r, c = 0..7), so a step needs only the pivot column's entries of its 8 rows and (by
+// symmetry) of its 8 columns -- 64 B instead of 256 B -- and the cyclic ownership keeps all 64 threads busy while
+// the live part of the matrix shrinks (block JR updates (8-JR)^2 of the 64 entries).
+//   registers  A[rp][c] = (A[ti + 16rp][tj + 8c], A[ti + 16rp + 8][tj + 8c])   (row pairs: a column of the tile is
+//              four packed registers, published with two 16-byte stores, no repacking)
+//   step j = 8*JR + jm: the eight threads with tj == jm publish column j into row j of Pall ([ti*8 + r] = entry
+//              of row ti + 8r), one barrier, then every thread does  A[m][n] -= (A[m][j]/d) * A[n][j]  on its live
+//              entries: the row multipliers arrive packed (one FFMA2-multiply by -1/d per pair), the column
+//              values are broadcast into both halves of a register.
+//   right-hand side: element m lives in ONE thread, (ti, tj) = (m % 8, m / 8), updated with one extra load.
+// The loop over jm is rolled (register indices depend on JR only): the eight blocks are a few KB of code.
+// Pall keeps every published column: row m of Pall is column m of L*D, read by the back-substitution
+// (thread = row again, as in ldlt64_rows).  The whole solve is one out-of-line function so that it gets the full
+// register budget: the kernel's loop state is saved around the call once per row instead of spilling per step.
+constexpr int kTcPallLd = 68;                         // floats per Pall row (16-byte aligned rows)
+
+template <int JR>
+__device__ __forceinline__ void ldlt64_tile_block(f32x2 (&A)[4][8], float& bb, uint32_t pTi, uint32_t pTj,
+                                                  uint32_t pMine, uint32_t Pall, uint32_t Y, int ti, int tj) {
+  constexpr int RP0 = JR / 2;                           // first live row pair
+#pragma unroll 1
+  for (int jm = 0; jm < 8; ++jm) {
+    const int j = 8 * JR + jm;
+    const uint32_t ro = (uint32_t)j * (kTcPallLd * 4);
+    const bool own = (tj == jm);
+    sts128x2_if(own, pTi + ro, A[0][JR], A[1][JR]);
+    sts128x2_if(own, pTi + ro + 16, A[2][JR], A[3][JR]);
+    sts32_if(ti == jm && tj == JR, Y + (uint32_t)j * 4u, bb);
+    bar_sync_64(1);
+    f32x2 w[4], lcp[4];
+    lds128x2(pTi + ro, w[0], w[1]);
+    lds128x2(pTi + ro + 16, w[2], w[3]);
+    lds128x2(pTj + ro, lcp[0], lcp[1]);
+    lds128x2(pTj + ro + 16, lcp[2], lcp[3]);
+    const float d = lds32(Pall + ro + (uint32_t)(jm * 8 + JR) * 4u);
+    const float yj = lds32(Y + (uint32_t)j * 4u);
+    const float lm = lds32(pMine + ro);
+    const float ninv = -__fdividef(1.0f, d);
+    const f32x2 ninv2 = pack2(ninv, ninv);
+#pragma unroll
+    for (int rp = RP0; rp < 4; ++rp) w[rp] = ffma2(w[rp], ninv2, 0ull);
+    {   // rows <= j are finished: zero multiplier (local row JR is finished iff ti <= jm; JR-1, if in the pair, always)
+      float lo = lo2(w[RP0]), hi = hi2(w[RP0]);
+      if (JR & 1) { lo = 0.f; hi = (ti > jm) ? hi : 0.f; }
+      else lo = (ti > jm) ? lo : 0.f;
+      w[RP0] = pack2(lo, hi);
+    }
+#pragma unroll
+    for (int c = JR; c < 8; ++c) {
+      float l = (c & 1) ? hi2(lcp[c / 2]) : lo2(lcp[c / 2]);
+      if (c == JR) l = (tj > jm) ? l : 0.f;             // columns <= j are finished
+      const f32x2 l2 = pack2(l, l);
+#pragma unroll
+      for (int rp = RP0; rp < 4; ++rp) A[rp][c] = ffma2(w[rp], l2, A[rp][c]);
+    }
+    const bool act = (tj > JR) || (tj == JR && ti > jm);   // my right-hand-side row ti + 8*tj is below the pivot
+    bb = act ? fmaf(lm * ninv, yj, bb) : bb;
+  }
+}
+
+// Gathers A = D_hh + D_lh + D_lh^T + lam*I (hand-over rows S1, S2 of stride kTcLDS) into the thread's tile, releases
+// the stage ring (__syncthreads: the producers wait there too), factors, substitutes back.  Returns x_s.
+__device__ __noinline__ float als64_solve_tile(uint32_t sS1, uint32_t sS2, uint32_t sB1, uint32_t sB2, uint32_t Pall,
+                                               float lam, int s) {
+  constexpr int LDS = kTcLDS;
+  const int ti = s >> 3, tj = s & 7, lane = s & 31;
+  const uint32_t Y = Pall + 64 * kTcPallLd * 4, Z = Y + 256, X = Z + 256;
+  f32x2 A[4][8];
+#pragma unroll
+  for (int rp = 0; rp < 4; ++rp) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int n = tj + 8 * c;
+      float v[2];
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int m = ti + 16 * rp + 8 * x;
+        const uint32_t mn = (uint32_t)(m * LDS + n) * 4u, nm = (uint32_t)(n * LDS + m) * 4u;
+        v[x] = lds32(sS1 + mn) + lds32(sS2 + mn) + lds32(sS2 + nm) + (m == n ? lam : 0.f);
+      }
+      A[rp][c] = pack2(v[0], v[1]);
+    }
+  }
+  float bb = lds32(sB1 + (uint32_t)(ti + 8 * tj) * 4u) + lds32(sB2 + (uint32_t)(ti + 8 * tj) * 4u);
+  __syncthreads();    // the stage ring (S1, S2 alias it) is free again: the producers start the next item
+  const uint32_t pTi = Pall + (uint32_t)ti * 32u, pTj = Pall + (uint32_t)tj * 32u, pMine = Pall + (uint32_t)(ti * 8 + tj) * 4u;
+  ldlt64_tile_block<0>(A, bb, pTi, pTj, pMine, Pall, Y, ti, tj);
+  ldlt64_tile_block<1>(A, bb, pTi, pTj, pMine, Pall, Y, ti, tj);
+  ldlt64_tile_block<2>(A, bb, pTi, pTj, pMine, Pall, Y, ti, tj);
+  ldlt64_tile_block<3>(A, bb, pTi, pTj, pMine, Pall, Y, ti, tj);
+  ldlt64_tile_block<4>(A, bb, pTi, pTj, pMine, Pall, Y, ti, tj);
+  ldlt64_tile_block<5>(A, bb, pTi, pTj, pMine, Pall, Y, ti, tj);
+  ldlt64_tile_block<6>(A, bb, pTi, pTj, pMine, Pall, Y, ti, tj);
+  ldlt64_tile_block<7>(A, bb, pTi, pTj, pMine, Pall, Y, ti, tj);
+  // z = L^-1 b: element ti + 8*tj sits in this thread; hand row m's entry to thread m
+  sts32(Z + (uint32_t)(ti + 8 * tj) * 4u, bb);
+  bar_sync_64(1);
+  const int m = s;
+  const uint32_t rowm = Pall + (uint32_t)m * (kTcPallLd * 4);
+  // entry j of column m of L*D: published by thread (j%8, m%8) at position (j%8)*8 + j/8
+  auto elem = [&](int j) -> float { return lds32(rowm + (uint32_t)((j & 7) * 8 + (j >> 3)) * 4u); };
+  float acc = lds32(Z + (uint32_t)m * 4u);
+  const float inv_d = __fdividef(1.0f, elem(m));
+  float x = 0.f;
+  if (m >= 32) {
+#pragma unroll
+    for (int j = 63; j >= 32; --j) {
+      const float lj = elem(j);
+      const float xj = __shfl_sync(0xffffffffu, acc * inv_d, j - 32);   // lane j-32 owns x_j
+      if (m == j) x = xj;
+      if (m < j) acc = fmaf(-lj, xj, acc);
+    }
+    sts32(X + (uint32_t)lane * 4u, x);
+  }
+  bar_sync_64(1);
+  if (m < 32) {
+#pragma unroll
+    for (int j = 63; j >= 32; --j) acc = fmaf(-elem(j), lds32(X + (uint32_t)(j - 32) * 4u), acc);
+#pragma unroll
+    for (int j = 31; j >= 0; --j) {
+      const float lj = elem(j);
+      const float xj = __shfl_sync(0xffffffffu, acc * inv_d, j);
+      if (m == j) x = xj;
+      if (m < j) acc = fmaf(-lj, xj, acc);
+    }
+  }
+  return x;
+}
+
 #ifndef HALS_TC_CTAS_PER_SM
 #define HALS_TC_CTAS_PER_SM 4
 #endif
@@ -212,15 +346,18 @@ als_tc64_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ va
                 const int32_t* __restrict__ item_row, const int64_t* __restrict__ item_begin,
                 const int32_t* __restrict__ item_len, const int32_t* __restrict__ item_slot,
                 int64_t n_items, float* __restrict__ workspace, int n_sm) {
-  constexpr int K = kTcK, KC = kTcKC, LD = kTcLD, LDP = kTcLDP;
+  constexpr int K = kTcK, KC = kTcKC, LDS = kTcLDS;
   extern __shared__ uint8_t smem_dyn[];
   __shared__ uint64_t mbar_free[kTcStages];
   __shared__ uint64_t mbar_acc;
   __shared__ uint32_t tmem_slot;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  float* P = reinterpret_cast<float*>(base + kTcStages * kTcStageBytes);   // published pivot rows (solver warps only)
-  float* S2 = reinterpret_cast<float*>(base);                              // l h^T block; aliases the stage ring
-  float* S2b = S2 + K * LD;
+  // solver scratch behind the stage ring: every published pivot column (16 KB) + y, z, x hand-over rows
+  const uint32_t sPall = umma::smem_u32(base + kTcStages * kTcStageBytes);
+  // hand-over of the accumulators to the solver tiles; aliases the stage ring (free between the item's last MMA
+  // and the producers' next gather): S1 = h h^T rows, S2 = l h^T rows (row stride 68 floats), then the two
+  // right-hand-side pieces
+  const uint32_t sS1 = umma::smem_u32(base), sS2 = sS1 + 64 * kTcLDS * 4, sB1 = sS2 + 64 * kTcLDS * 4, sB2 = sB1 + 256;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // Roles alternate with the CTA parity so that the solver warps of the co-resident CTAs spread
@@ -340,47 +477,42 @@ als_tc64_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ va
     umma::tmem_ld32(ta + 32, a + 32);
     umma::tmem_ld16(ta + 64, e);
     umma::fence_before_sync();
-    if (producer) {     // l h^T rows go through shared memory
-      float* r2 = S2 + ptid * LD;
+    {   // both halves go through shared memory: h h^T rows from the solver pair, l h^T rows from the producers
+      const uint32_t dstrow = (producer ? sS2 + (uint32_t)ptid * (LDS * 4) : sS1 + (uint32_t)stid * (LDS * 4));
 #pragma unroll
-      for (int n = 0; n < 64; ++n) r2[n] = a[n];
-      S2b[ptid] = e[0];
+      for (int n = 0; n < 64; n += 4) sts128(dstrow + n * 4, a[n], a[n + 1], a[n + 2], a[n + 3]);
+      if (producer) sts32(sB2 + ptid * 4, e[0]);
+      else sts32(sB1 + stid * 4, e[0] + e[1]);
     }
     HALS_PF(2);   // drain
     __syncthreads();
     HALS_PF(3);   // wait at sync 1
-    if (!producer) {
+    if (producer) {
+      HALS_PF(4);
+      __syncthreads();  // the stage ring is free again once the solver pair has read the hand-over rows
+      HALS_PF(5);
+    } else if (slot >= 0) {
+      // slice of a long row: thread = row m, park (A, b, n) in the slot (same layout as the SIMT path)
       const int m = stid;
-      const float lam = slot >= 0 ? 0.f : reg * (float)len;
+      float* W = workspace + (size_t)slot * ((size_t)K * K + K + 4);
 #pragma unroll
-      for (int n = 0; n < 64; ++n) a[n] += S2[m * LD + n] + S2[n * LD + m] + (n == m ? lam : 0.f);
-      a[64] = e[0] + e[1] + S2b[m];
-    }
-    HALS_PF(4);   // combine
-    __syncthreads();    // S2 (stage ring) is free again: the producers may start the next item
-    HALS_PF(5);   // wait at sync 2
-    if (!producer) {
-      const int m = stid;
-      if (slot >= 0) {
-        // slice of a long row: park (A, b, n) in the slot (same layout as the SIMT path)
-        float* W = workspace + (size_t)slot * ((size_t)K * K + K + 4);
-#pragma unroll
-        for (int n = 0; n < 64; n += 4)
-          *reinterpret_cast<float4*>(W + m * K + n) = make_float4(a[n], a[n + 1], a[n + 2], a[n + 3]);
-        W[K * K + m] = a[64];
-        if (m == 0) W[K * K + K] = (float)len;
-      } else {
-        f32x2 ap[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ap[i] = pack2(a[2 * i], a[2 * i + 1]);
-#ifdef HALS_TC_PROFILE
-        const float x = ldlt64_rows<LDP>(ap, a[64], umma::smem_u32(P), m, pfs);
-#else
-        const float x = ldlt64_rows<LDP>(ap, a[64], umma::smem_u32(P), m);
-#endif
-        dst[(int64_t)row * K + m] = x;
-        bar_sync_64(1);   // P is reused by the next item
+      for (int n = 0; n < 64; n += 4) {
+        const float4 q = lds128(sS2 + (uint32_t)m * (LDS * 4) + n * 4);
+        *reinterpret_cast<float4*>(W + m * K + n) =
+            make_float4(a[n] + q.x + lds32(sS2 + (uint32_t)(n) * (LDS * 4) + m * 4),
+                        a[n + 1] + q.y + lds32(sS2 + (uint32_t)(n + 1) * (LDS * 4) + m * 4),
+                        a[n + 2] + q.z + lds32(sS2 + (uint32_t)(n + 2) * (LDS * 4) + m * 4),
+                        a[n + 3] + q.w + lds32(sS2 + (uint32_t)(n + 3) * (LDS * 4) + m * 4));
       }
+      W[K * K + m] = e[0] + e[1] + lds32(sB2 + m * 4);
+      if (m == 0) W[K * K + K] = (float)len;
+      HALS_PF(4);
+      __syncthreads();
+      HALS_PF(5);
+    } else {
+      const float x = als64_solve_tile(sS1, sS2, sB1, sB2, sPall, reg * (float)len, stid);   // contains the __syncthreads
+      dst[(int64_t)row * K + stid] = x;
+      bar_sync_64(1);   // the solver scratch is reused by the next item
     }
     HALS_PF(6);   // solve
   }
@@ -473,7 +605,8 @@ int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* sr
   const int64_t nthreads = n_src * (kTcK / 8);
   split_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(src, n_src, kTcK, hl);
   HALS_LAUNCH_CHECK();
-  const size_t smem = (size_t)kTcStages * kTcStageBytes + kTcS1Floats * sizeof(float) + 1024;
+  const size_t smem = (size_t)kTcStages * kTcStageBytes + kTcSolverBytes + 1024;
+  static_assert(kTcStages * kTcStageBytes >= 2 * 64 * kTcLDS * 4 + 512, "accumulator hand-over must fit in the stage ring");
   HALS_CUDA(cudaFuncSetAttribute(als_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const int grid_mult = [] { const char* e = getenv("HALS_TC_GRID_MULT"); return e ? atoi(e) : HALS_TC_CTAS_PER_SM; }();
   int64_t grid = grid_mult * (int64_t)sm_count();
