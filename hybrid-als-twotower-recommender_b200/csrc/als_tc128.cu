@@ -36,8 +36,8 @@ constexpr int k8StageBytes = 5 * k8Blk;     // H0 | H1 | L0 | L1 | R
 constexpr int k8Threads = 320;
 constexpr int k8LDH = 129;                  // leading dimension of the h l^T staging buffer
 constexpr int k8LDP = 132;                  // pivot slot: 128 window floats + rhs (+ pad to 16 B)
-constexpr int k8GroupFloats = 128 * k8LDH + 2 * k8LDP + 128;   // HL buffer + 2 pivot slots + x hand-over
-constexpr int k8GroupBytes = (k8GroupFloats * 4 + 15) / 16 * 16;
+constexpr int k8LDC = 132;                  // row stride of the hand-over matrix C / of Pall (16-byte aligned rows)
+constexpr int k8GroupBytes = 128 * k8LDC * 4 + 4 * 512;        // C (aliased by Pall) + b, y, z, x rows
 constexpr size_t k8SlotFloats = (size_t)k8K * k8K + k8K + 4;
 
 // 128 x 128 SPD solve by one solver group (4 warps, thread = row m, rb = m / 32).
@@ -138,6 +138,136 @@ __device__ __forceinline__ float ldlt128_rows(f32x2 (&ap)[64], float rhs, uint32
       sts32(X + m * 4, x);
     }
     if (w > 0) bar_sync_n(bar_base, 128);
+  }
+  return x;
+}
+
+// ---- 2-D cyclic register tiling (main kernel) -----------------------------------------------------------
+// als_tc.cu's tile solver at rank 128: the 128 threads of a solver group form a 16 x 8 grid, thread (ti, tj) owns
+// A[ti + 16r][tj + 8c] (r = 0..7, c = 0..15; 64 packed registers, as many as the row layout needed), so a step
+// moves 96 B of pivot data per thread instead of 512 B and updates only the live part of the tile.
+//   registers   A[rp][c] = (A[ti + 32rp][tj + 8c], A[ti + 32rp + 16][tj + 8c])
+//   Pall row j  [ti*8 + r] = A[ti + 16r][j]  (published by the 16 threads with tj == j % 8): a thread reads its 8 row
+//               entries at [ti*8 ..], the entries of its even local columns at [tj*8 ..] and of its odd ones at
+//               [(tj+8)*8 ..]  (column n = tj + 8c is row n of the symmetric matrix: n % 16 = tj + 8(c&1), n / 16 = c/2)
+//   rhs         element m lives in thread (m % 16, m / 16)
+// Blocks of 8 pivots (JC = j / 8) fix every register index; the loop over the pivot inside a block is rolled.
+template <int JC>
+__device__ __forceinline__ void ldlt128_tile_block(f32x2 (&A)[4][16], float& bb, uint32_t pTi, uint32_t pTjE, uint32_t pTjO,
+                                                   uint32_t pMine, uint32_t Pall, uint32_t Y, int ti, int tj, int bar) {
+  constexpr int JR = JC / 2;                            // local row index of this block's pivot rows
+  constexpr int RP0 = JR / 2;                           // first live row pair
+  constexpr int TI0 = 8 * (JC & 1);                     // pivot j = 8 JC + jm is row-owned by ti == TI0 + jm
+#pragma unroll 1
+  for (int jm = 0; jm < 8; ++jm) {
+    const int j = 8 * JC + jm;
+    const uint32_t ro = (uint32_t)j * (k8LDC * 4);
+    const bool own = (tj == jm);
+    sts128x2_if(own, pTi + ro, A[0][JC], A[1][JC]);
+    sts128x2_if(own, pTi + ro + 16, A[2][JC], A[3][JC]);
+    sts32_if(ti == TI0 + jm && tj == JR, Y + (uint32_t)j * 4u, bb);
+    bar_sync_n(bar, 128);
+    f32x2 w[4], le[4], lo[4];
+    lds128x2(pTi + ro, w[0], w[1]);
+    lds128x2(pTi + ro + 16, w[2], w[3]);
+    // le[q] = local columns 4q, 4q+2 ; lo[q] = local columns 4q+1, 4q+3 ; dead quads are not loaded
+    if (2 >= JC) lds128x2(pTjE + ro, le[0], le[1]); else if (6 >= JC) le[1] = lds64x2(pTjE + ro + 8);
+    if (10 >= JC) lds128x2(pTjE + ro + 16, le[2], le[3]); else if (14 >= JC) le[3] = lds64x2(pTjE + ro + 24);
+    if (3 >= JC) lds128x2(pTjO + ro, lo[0], lo[1]); else if (7 >= JC) lo[1] = lds64x2(pTjO + ro + 8);
+    if (11 >= JC) lds128x2(pTjO + ro + 16, lo[2], lo[3]); else lo[3] = lds64x2(pTjO + ro + 24);
+    const float d = lds32(Pall + ro + (uint32_t)((TI0 + jm) * 8 + JR) * 4u);
+    const float yj = lds32(Y + (uint32_t)j * 4u);
+    const float lm = lds32(pMine + ro);
+    const float ninv = -__fdividef(1.0f, d);
+    const f32x2 ninv2 = pack2(ninv, ninv);
+#pragma unroll
+    for (int rp = RP0; rp < 4; ++rp) w[rp] = ffma2(w[rp], ninv2, 0ull);
+    {   // rows <= j are finished: zero multiplier (local row JR iff ti <= TI0 + jm; JR-1, if in the pair, always)
+      float l0 = lo2(w[RP0]), h0 = hi2(w[RP0]);
+      if (JR & 1) { l0 = 0.f; h0 = (ti > TI0 + jm) ? h0 : 0.f; }
+      else l0 = (ti > TI0 + jm) ? l0 : 0.f;
+      w[RP0] = pack2(l0, h0);
+    }
+#pragma unroll
+    for (int c = JC; c < 16; ++c) {
+      const int q = c >> 2;
+      const f32x2 src = (c & 1) ? lo[q] : le[q];
+      float l = (c & 2) ? hi2(src) : lo2(src);
+      if (c == JC) l = (tj > jm) ? l : 0.f;             // columns <= j are finished
+      const f32x2 l2 = pack2(l, l);
+#pragma unroll
+      for (int rp = RP0; rp < 4; ++rp) A[rp][c] = ffma2(w[rp], l2, A[rp][c]);
+    }
+    const bool act = (tj > JR) || (tj == JR && ti > TI0 + jm);   // my right-hand-side row ti + 16*tj is below the pivot
+    bb = act ? fmaf(lm * ninv, yj, bb) : bb;
+  }
+}
+
+// C (row stride k8LDC): rows m of 0.5*D_hh + D_hl, so that A = C + C^T; B: right-hand side.  Pall aliases C.
+// s = thread index inside the solver group (0..127); bar = the group's named barrier.  Returns x_s.
+__device__ __noinline__ float als128_solve_tile(uint32_t C, uint32_t B, float lam, int s, int bar) {
+  const int ti = s >> 3, tj = s & 7, lane = s & 31, wq = s >> 5;
+  const uint32_t Pall = C, Y = B + 512, Z = Y + 512, X = Z + 512;
+  f32x2 A[4][16];
+#pragma unroll
+  for (int rp = 0; rp < 4; ++rp) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int n = tj + 8 * c;
+      float v[2];
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int m = ti + 32 * rp + 16 * x;
+        v[x] = lds32(C + (uint32_t)(m * k8LDC + n) * 4u) + lds32(C + (uint32_t)(n * k8LDC + m) * 4u) + (m == n ? lam : 0.f);
+      }
+      A[rp][c] = pack2(v[0], v[1]);
+    }
+  }
+  float bb = lds32(B + (uint32_t)(ti + 16 * tj) * 4u);
+  bar_sync_n(bar, 128);                                  // every thread holds its tile: Pall may overwrite C
+  const uint32_t pTi = Pall + (uint32_t)ti * 32u, pTjE = Pall + (uint32_t)tj * 32u, pTjO = Pall + (uint32_t)(tj + 8) * 32u;
+  const uint32_t pMine = Pall + (uint32_t)(ti * 8 + tj) * 4u;
+  ldlt128_tile_block<0>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<1>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<2>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<3>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<4>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<5>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<6>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<7>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<8>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<9>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<10>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<11>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<12>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<13>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<14>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  ldlt128_tile_block<15>(A, bb, pTi, pTjE, pTjO, pMine, Pall, Y, ti, tj, bar);
+  // z = L^-1 b: element ti + 16*tj sits in this thread; hand row m's entry to thread m = s
+  sts32(Z + (uint32_t)(ti + 16 * tj) * 4u, bb);
+  bar_sync_n(bar, 128);
+  const int m = s;
+  const uint32_t rowm = Pall + (uint32_t)m * (k8LDC * 4);
+  // entry j of column m of L*D sits at position (j % 16) * 8 + j / 16 of Pall row m
+  auto elem = [&](int j) -> float { return lds32(rowm + (uint32_t)((j & 15) * 8 + (j >> 4)) * 4u); };
+  float acc = lds32(Z + (uint32_t)m * 4u), x = 0.f;
+  const float inv_d = __fdividef(1.0f, elem(m));
+  // x_c = (z_c - sum_{j>c} (L D)[j][c] x_j) / d_c, last warp first
+#pragma unroll 1
+  for (int wv = 3; wv >= 0; --wv) {
+    if (wq == wv) {
+#pragma unroll 8
+      for (int j = 127; j >= 32 * (wv + 1); --j) acc = fmaf(-elem(j), lds32(X + (uint32_t)j * 4u), acc);
+#pragma unroll 8
+      for (int jl = 31; jl >= 0; --jl) {                 // own block: pivot 32 wv + jl lives in lane jl
+        const float lj = elem(32 * wv + jl);
+        const float xj = __shfl_sync(0xffffffffu, acc * inv_d, jl);
+        if (lane == jl) x = xj;
+        if (lane < jl) acc = fmaf(-lj, xj, acc);
+      }
+      sts32(X + (uint32_t)m * 4u, x);
+    }
+    if (wv > 0) bar_sync_n(bar, 128);
   }
   return x;
 }
@@ -262,10 +392,9 @@ als_tc128_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ v
     als128_producer(base, sbase, tmem, mbar_free, mbar_acc, &mbar_tmem_free, colidx, vals, src_hl, item_begin, item_len, n_items);
   } else {
     // ================================================================ solver groups
-    float* HL = reinterpret_cast<float*>(base + k8Stages * k8StageBytes + group * k8GroupBytes);
-    const uint32_t P = umma::smem_u32(HL + 128 * k8LDH);
-    const uint32_t X = P + 2 * k8LDP * 4;
-    const int bar_base = 2 + 6 * group;                  // named barriers 2..7 (group A) / 8..13 (group B): 3 phase + 3 hand-shake
+    const uint32_t sC = umma::smem_u32(base + k8Stages * k8StageBytes + group * k8GroupBytes);   // C, later Pall
+    const uint32_t sB = sC + 128 * k8LDC * 4;             // b | y | z | x rows (128 floats each)
+    const int bar = 2 + group;                            // named barrier of this group (1 = producers)
     const uint32_t ta = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     uint32_t it = 0, mine = 0;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -276,53 +405,43 @@ als_tc128_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ v
       umma::mbar_wait(&mbar_acc[group], mine & 1);
       ++mine;
       umma::fence_after_sync();
-      // h l^T block -> shared (row m), so that its transpose can be read back
-      float e1[16], e2[16];
+      // drain: row m of C = D_hh / 2 + D_hl goes to shared memory (A = C + C^T), then the accumulator is free
       {
-        float v[32];
+        float v[32], u[32];
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
-          umma::tmem_ld32(ta + 128 + c0, v);
+          umma::tmem_ld32(ta + c0, v);
+          umma::tmem_ld32(ta + 128 + c0, u);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) HL[m * k8LDH + c0 + i] = v[i];
+          for (int i = 0; i < 32; i += 4)
+            sts128(sC + (uint32_t)(m * k8LDC + c0 + i) * 4u, fmaf(0.5f, v[i], u[i]), fmaf(0.5f, v[i + 1], u[i + 1]),
+                   fmaf(0.5f, v[i + 2], u[i + 2]), fmaf(0.5f, v[i + 3], u[i + 3]));
         }
+        float e1[16], e2[16];
         umma::tmem_ld16(ta + 256, e1);
         umma::tmem_ld16(ta + 272, e2);
+        sts32(sB + (uint32_t)m * 4u, e1[0] + e1[1] + e2[0]);
       }
-      bar_sync_n(bar_base, 128);
-      const float lam = slot >= 0 ? 0.f : reg * (float)len;
-      f32x2 ap[64];
-      {
-        float v[32];
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          umma::tmem_ld32(ta + c0, v);
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const int n = c0 + i;
-            const float a0 = v[i] + HL[m * k8LDH + n] + HL[n * k8LDH + m] + (n == m ? lam : 0.f);
-            const float a1 = v[i + 1] + HL[m * k8LDH + n + 1] + HL[(n + 1) * k8LDH + m] + (n + 1 == m ? lam : 0.f);
-            ap[n / 2] = pack2(a0, a1);
-          }
-        }
-      }
-      const float bm = e1[0] + e1[1] + e2[0];
       umma::fence_before_sync();
-      bar_sync_n(bar_base, 128);                          // every TMEM / HL read of this item is done
+      bar_sync_n(bar, 128);                               // C complete, every TMEM read of this item done
       if (m == 0) umma::mbar_arrive(&mbar_tmem_free);
       if (slot >= 0) {
+        // slice of a long row: thread = row m parks (A, b, n) in the slot (same layout as the SIMT path)
         float* W = workspace + (size_t)slot * k8SlotFloats;
-#pragma unroll
-        for (int n = 0; n < 128; n += 4)
+#pragma unroll 4
+        for (int n = 0; n < 128; n += 4) {
+          const float4 q = lds128(sC + (uint32_t)(m * k8LDC + n) * 4u);
           *reinterpret_cast<float4*>(W + m * K + n) =
-              make_float4(lo2(ap[n / 2]), hi2(ap[n / 2]), lo2(ap[n / 2 + 1]), hi2(ap[n / 2 + 1]));
-        W[K * K + m] = bm;
+              make_float4(q.x + lds32(sC + (uint32_t)((n) * k8LDC + m) * 4u), q.y + lds32(sC + (uint32_t)((n + 1) * k8LDC + m) * 4u),
+                          q.z + lds32(sC + (uint32_t)((n + 2) * k8LDC + m) * 4u), q.w + lds32(sC + (uint32_t)((n + 3) * k8LDC + m) * 4u));
+        }
+        W[K * K + m] = lds32(sB + (uint32_t)m * 4u);
         if (m == 0) W[K * K + K] = (float)len;
       } else {
-        const float x = ldlt128_rows(ap, bm, P, X, m, bar_base);
+        const float x = als128_solve_tile(sC, sB, reg * (float)len, m, bar);
         dst[(int64_t)row * K + m] = x;
-        bar_sync_n(bar_base, 128);                        // pivot slots / x hand-over are reused by the next item
       }
+      bar_sync_n(bar, 128);                               // C / Pall and the hand-over rows are reused by the next item
     }
   }
 
