@@ -228,15 +228,21 @@ template <int JR>
 __device__ __forceinline__ void ldlt64_tile_block(f32x2 (&A)[4][8], float& bb, uint32_t pTi, uint32_t pTj,
                                                   uint32_t pMine, uint32_t Pall, uint32_t Y, int ti, int tj) {
   constexpr int RP0 = JR / 2;                           // first live row pair
+  // Software pipeline: the barrier that makes column j+1 visible is issued right after its owners publish it,
+  // BEFORE the bulk of step j's update (BAR.SYNC blocks only at the next shared-memory access), so the barrier
+  // latency and the store drain hide behind FFMA2 work instead of sitting on the 64-step dependency chain.
+  {
+    const uint32_t ro = (uint32_t)(8 * JR) * (kTcPallLd * 4);
+    const bool own = (tj == 0);
+    sts128x2_if(own, pTi + ro, A[0][JR], A[1][JR]);
+    sts128x2_if(own, pTi + ro + 16, A[2][JR], A[3][JR]);
+    sts32_if(ti == 0 && tj == JR, Y + (uint32_t)(8 * JR) * 4u, bb);
+    bar_sync_64(1);
+  }
 #pragma unroll 1
   for (int jm = 0; jm < 8; ++jm) {
     const int j = 8 * JR + jm;
     const uint32_t ro = (uint32_t)j * (kTcPallLd * 4);
-    const bool own = (tj == jm);
-    sts128x2_if(own, pTi + ro, A[0][JR], A[1][JR]);
-    sts128x2_if(own, pTi + ro + 16, A[2][JR], A[3][JR]);
-    sts32_if(ti == jm && tj == JR, Y + (uint32_t)j * 4u, bb);
-    bar_sync_64(1);
     f32x2 w[4], lcp[4];
     lds128x2(pTi + ro, w[0], w[1]);
     lds128x2(pTi + ro + 16, w[2], w[3]);
@@ -255,16 +261,30 @@ __device__ __forceinline__ void ldlt64_tile_block(f32x2 (&A)[4][8], float& bb, u
       else lo = (ti > jm) ? lo : 0.f;
       w[RP0] = pack2(lo, hi);
     }
+    {   // the block's pivot column first (columns <= j are finished: zero for tj <= jm) ...
+      float l = (JR & 1) ? hi2(lcp[JR / 2]) : lo2(lcp[JR / 2]);
+      l = (tj > jm) ? l : 0.f;
+      const f32x2 l2 = pack2(l, l);
 #pragma unroll
-    for (int c = JR; c < 8; ++c) {
-      float l = (c & 1) ? hi2(lcp[c / 2]) : lo2(lcp[c / 2]);
-      if (c == JR) l = (tj > jm) ? l : 0.f;             // columns <= j are finished
+      for (int rp = RP0; rp < 4; ++rp) A[rp][JR] = ffma2(w[rp], l2, A[rp][JR]);
+    }
+    const bool act = (tj > JR) || (tj == JR && ti > jm);   // my right-hand-side row ti + 8*tj is below the pivot
+    bb = act ? fmaf(lm * ninv, yj, bb) : bb;
+    if (jm < 7) {   // ... so that column j+1 goes out before the rest of the update
+      const bool own = (tj == jm + 1);
+      const uint32_t r1 = ro + kTcPallLd * 4;
+      sts128x2_if(own, pTi + r1, A[0][JR], A[1][JR]);
+      sts128x2_if(own, pTi + r1 + 16, A[2][JR], A[3][JR]);
+      sts32_if(ti == jm + 1 && tj == JR, Y + (uint32_t)(j + 1) * 4u, bb);
+      bar_sync_64(1);
+    }
+#pragma unroll
+    for (int c = JR + 1; c < 8; ++c) {
+      const float l = (c & 1) ? hi2(lcp[c / 2]) : lo2(lcp[c / 2]);
       const f32x2 l2 = pack2(l, l);
 #pragma unroll
       for (int rp = RP0; rp < 4; ++rp) A[rp][c] = ffma2(w[rp], l2, A[rp][c]);
     }
-    const bool act = (tj > JR) || (tj == JR && ti > jm);   // my right-hand-side row ti + 8*tj is below the pivot
-    bb = act ? fmaf(lm * ninv, yj, bb) : bb;
   }
 }
 
