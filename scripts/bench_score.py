@@ -23,7 +23,7 @@ for rep in range(int(os.environ.get('REPS', '3'))):
     pairs = U * I
     print(json.dumps({"U": U, "I": I, "k": k, "ms_extrema": t1, "ms_topk": t2, "pairs_per_s": pairs / ((t1 + t2) * 1e-3),
                       "tflops_pass1": pairs * 2 * (ka + kt) / (t1 * 1e-3) / 1e12, "tflops_pass2": pairs * 2 * (ka + kt) / (t2 * 1e-3) / 1e12,
-                      "flagged_pass2": f2}))
+                      "flagged_pass1": f1, "flagged_pass2": f2}))
 # spot check against fp64 on a few users
 sel = torch.arange(0, U, max(U // 4, 1), device="cuda")[:4]
 Sa = (Ua[sel].double() @ Ia.double().T); St = (Ut[sel].double() @ It.double().T)
