@@ -80,16 +80,17 @@ class AlsEngine:
         ratings = torch.as_tensor(ratings).to(self.device, torch.float32)
         self.nnz_total = int(users.numel())
         # nnz-balanced contiguous row ranges (identical on every rank: computed from global counts)
-        ucnt = torch.bincount(users.to(torch.int64), minlength=n_users).cpu().numpy()
-        icnt = torch.bincount(items.to(torch.int64), minlength=n_items).cpu().numpy()
+        ucnt_d = torch.bincount(users.to(torch.int64), minlength=n_users)
+        icnt_d = torch.bincount(items.to(torch.int64), minlength=n_items)
+        ucnt, icnt = ucnt_d.cpu().numpy(), icnt_d.cpu().numpy()
         self.user_bounds = balanced_row_bounds(ucnt, world)
         self.item_bounds = balanced_row_bounds(icnt, world)
         self.user_present = torch.from_numpy(ucnt > 0).to(self.device)
         self.item_present = torch.from_numpy(icnt > 0).to(self.device)
         ub, ue = int(self.user_bounds[dist_rank]), int(self.user_bounds[dist_rank + 1])
         ib, ie = int(self.item_bounds[dist_rank]), int(self.item_bounds[dist_rank + 1])
-        self.R = build_csr(users, items, ratings, n_users, ub, ue)       # user rows -> item columns
-        self.Rt = build_csr(items, users, ratings, n_items, ib, ie)      # item rows -> user columns
+        self.R = build_csr(users, items, ratings, n_users, ub, ue, counts=ucnt_d)    # user rows -> item columns
+        self.Rt = build_csr(items, users, ratings, n_items, ib, ie, counts=icnt_d)   # item rows -> user columns
         self.plan_R = self.plan_Rt = None
         if make_plans:
             self.plan_R = AlsPlanHandle(self.R, self.k, seg_len, n_src=n_items)

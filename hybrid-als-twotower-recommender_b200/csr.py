@@ -49,21 +49,26 @@ def balanced_row_bounds(counts: np.ndarray, world: int) -> np.ndarray:
 
 
 def build_csr(rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n_rows: int,
-              row_begin: int = 0, row_end: int | None = None) -> CsrShard:
+              row_begin: int = 0, row_end: int | None = None, counts: torch.Tensor | None = None) -> CsrShard:
     """Stable COO -> CSR for rows in [row_begin, row_end): the ratings of a row keep their
-    input order, duplicates are kept (Spark does not merge them)."""
+    input order, duplicates are kept (Spark does not merge them).  `counts` (int64 [n_rows], device) may pass
+    the per-row rating counts of the WHOLE matrix when the caller already has them."""
     if row_end is None:
         row_end = n_rows
     dev = rows.device
-    rows = rows.to(torch.int64)
-    if row_begin != 0 or row_end != n_rows:
+    whole = row_begin == 0 and row_end == n_rows
+    if not whole:
         keep = (rows >= row_begin) & (rows < row_end)
         rows, cols, vals = rows[keep], cols[keep], vals[keep]
-    local = rows - row_begin
-    order = torch.argsort(local, stable=True)
-    counts = torch.bincount(local, minlength=row_end - row_begin)
+    # 32-bit sort keys: the radix sort moves half the bytes of an int64 sort
+    local = (rows - row_begin).to(torch.int32) if not whole else rows.to(torch.int32)
+    order = torch.sort(local, stable=True).indices
+    if counts is not None:
+        cnt = counts[row_begin:row_end]
+    else:
+        cnt = torch.bincount(local.to(torch.int64), minlength=row_end - row_begin)
     rowptr = torch.zeros(row_end - row_begin + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(counts, 0, out=rowptr[1:])
+    torch.cumsum(cnt, 0, out=rowptr[1:])
     return CsrShard(row_begin, row_end, n_rows, rowptr, cols[order].to(torch.int32).contiguous(),
                     vals[order].to(torch.float32).contiguous(), rowptr.cpu().numpy())
 
