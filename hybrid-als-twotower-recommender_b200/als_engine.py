@@ -20,29 +20,38 @@ def _dist():
     return dist if (dist.is_available() and dist.is_initialized()) else None
 
 
-def all_gather_rows(full: torch.Tensor, bounds, rank: int, world: int, group=None):
+def all_gather_rows(full: torch.Tensor, bounds, rank: int, world: int, group=None, cache: dict | None = None):
     """All-gather of uneven contiguous row shards of `full` ([n,k], every rank holds the whole
     buffer, its own rows freshly written).  Shards are padded to the largest one so a single
-    equal-size all-gather moves them (NCCL ring/NVLS over NVLink), then unpacked in place."""
+    equal-size all-gather moves them (NCCL ring/NVLS over NVLink), then one row gather unpacks
+    them in place.  `cache` (a dict owned by the caller) keeps the staging buffers and the unpack
+    index between calls: three launches per call instead of a dozen, no allocation."""
     dist = _dist()
     if dist is None or world == 1:
         return
     k = full.shape[1]
-    sizes = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
-    mx = max(sizes)
-    if mx == 0:
-        return
-    send = torch.zeros((mx, k), dtype=full.dtype, device=full.device)
-    send[: sizes[rank]] = full[int(bounds[rank]): int(bounds[rank + 1])]
-    recv = torch.empty((world, mx, k), dtype=full.dtype, device=full.device)
+    key = (full.data_ptr(), tuple(int(b) for b in bounds), k)
+    st = cache.get(key) if cache is not None else None
+    if st is None:
+        sizes = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
+        mx = max(sizes)
+        if mx == 0:
+            return
+        # row n of `full` lives at recv[(owner, n - bounds[owner])]
+        idx = torch.cat([torch.arange(sizes[r], dtype=torch.int64) + r * mx for r in range(world)]).to(full.device)
+        st = {"sizes": sizes, "mx": mx, "idx": idx,
+              "send": torch.zeros((mx, k), dtype=full.dtype, device=full.device),
+              "recv": torch.empty((world * mx, k), dtype=full.dtype, device=full.device)}
+        if cache is not None:
+            cache[key] = st
+    sizes, mx, send, recv = st["sizes"], st["mx"], st["send"], st["recv"]
+    send[: sizes[rank]].copy_(full[int(bounds[rank]): int(bounds[rank + 1])])
     if full.is_cuda:
-        dist.all_gather_into_tensor(recv.view(world * mx, k), send, group=group)
+        dist.all_gather_into_tensor(recv, send, group=group)
     else:  # gloo (CPU tests)
-        parts = list(recv.unbind(0))
+        parts = list(recv.view(world, mx, k).unbind(0))
         dist.all_gather(parts, send, group=group)
-    for r in range(world):
-        if r != rank and sizes[r]:
-            full[int(bounds[r]): int(bounds[r + 1])] = recv[r, : sizes[r]]
+    torch.index_select(recv, 0, st["idx"], out=full)
 
 
 def native_half_step(shard: CsrShard, plan: AlsPlanHandle, src: torch.Tensor, dst_full: torch.Tensor,
@@ -99,6 +108,7 @@ class AlsEngine:
         self.Y = torch.zeros((n_items, self.k), dtype=torch.float32, device=self.device)
         self.gram = None
         self.gram_ws = None
+        self._gather_cache = {}
         if self.implicit:
             self.gram = torch.zeros((self.k, self.k), dtype=torch.float32, device=self.device)
             if self.device.type == "cuda":
@@ -129,12 +139,12 @@ class AlsEngine:
     def item_half_step(self):
         self._half_step(self.Rt, self.plan_Rt, self.X, self.Y, self.k, self.reg, self.implicit, self.alpha,
                         self._gram_of(self.X))
-        all_gather_rows(self.Y, self.item_bounds, self.rank, self.world)
+        all_gather_rows(self.Y, self.item_bounds, self.rank, self.world, cache=self._gather_cache)
 
     def user_half_step(self):
         self._half_step(self.R, self.plan_R, self.Y, self.X, self.k, self.reg, self.implicit, self.alpha,
                         self._gram_of(self.Y))
-        all_gather_rows(self.X, self.user_bounds, self.rank, self.world)
+        all_gather_rows(self.X, self.user_bounds, self.rank, self.world, cache=self._gather_cache)
 
     def sweep(self):
         self.item_half_step()

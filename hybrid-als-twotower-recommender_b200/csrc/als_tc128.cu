@@ -158,15 +158,20 @@ __device__ __forceinline__ void ldlt128_tile_block(f32x2 (&A)[4][16], float& bb,
   constexpr int JR = JC / 2;                            // local row index of this block's pivot rows
   constexpr int RP0 = JR / 2;                           // first live row pair
   constexpr int TI0 = 8 * (JC & 1);                     // pivot j = 8 JC + jm is row-owned by ti == TI0 + jm
+  // Software pipeline (as in als_tc.cu): column j+1 is published, and the barrier issued, before the bulk of step
+  // j's update, so the barrier latency hides behind FFMA2 work.
+  {
+    const uint32_t ro = (uint32_t)(8 * JC) * (k8LDC * 4);
+    const bool own = (tj == 0);
+    sts128x2_if(own, pTi + ro, A[0][JC], A[1][JC]);
+    sts128x2_if(own, pTi + ro + 16, A[2][JC], A[3][JC]);
+    sts32_if(ti == TI0 && tj == JR, Y + (uint32_t)(8 * JC) * 4u, bb);
+    bar_sync_n(bar, 128);
+  }
 #pragma unroll 1
   for (int jm = 0; jm < 8; ++jm) {
     const int j = 8 * JC + jm;
     const uint32_t ro = (uint32_t)j * (k8LDC * 4);
-    const bool own = (tj == jm);
-    sts128x2_if(own, pTi + ro, A[0][JC], A[1][JC]);
-    sts128x2_if(own, pTi + ro + 16, A[2][JC], A[3][JC]);
-    sts32_if(ti == TI0 + jm && tj == JR, Y + (uint32_t)j * 4u, bb);
-    bar_sync_n(bar, 128);
     f32x2 w[4], le[4], lo[4];
     lds128x2(pTi + ro, w[0], w[1]);
     lds128x2(pTi + ro + 16, w[2], w[3]);
@@ -188,18 +193,33 @@ __device__ __forceinline__ void ldlt128_tile_block(f32x2 (&A)[4][16], float& bb,
       else l0 = (ti > TI0 + jm) ? l0 : 0.f;
       w[RP0] = pack2(l0, h0);
     }
+    auto colval = [&](int c) -> float {
+      const f32x2 src = (c & 1) ? lo[c >> 2] : le[c >> 2];
+      return (c & 2) ? hi2(src) : lo2(src);
+    };
+    {   // the block's pivot column first (columns <= j are finished: zero for tj <= jm) ...
+      const float l = (tj > jm) ? colval(JC) : 0.f;
+      const f32x2 l2 = pack2(l, l);
 #pragma unroll
-    for (int c = JC; c < 16; ++c) {
-      const int q = c >> 2;
-      const f32x2 src = (c & 1) ? lo[q] : le[q];
-      float l = (c & 2) ? hi2(src) : lo2(src);
-      if (c == JC) l = (tj > jm) ? l : 0.f;             // columns <= j are finished
+      for (int rp = RP0; rp < 4; ++rp) A[rp][JC] = ffma2(w[rp], l2, A[rp][JC]);
+    }
+    const bool act = (tj > JR) || (tj == JR && ti > TI0 + jm);   // my right-hand-side row ti + 16*tj is below the pivot
+    bb = act ? fmaf(lm * ninv, yj, bb) : bb;
+    if (jm < 7) {   // ... so that column j+1 goes out before the rest of the update
+      const bool own = (tj == jm + 1);
+      const uint32_t r1 = ro + k8LDC * 4;
+      sts128x2_if(own, pTi + r1, A[0][JC], A[1][JC]);
+      sts128x2_if(own, pTi + r1 + 16, A[2][JC], A[3][JC]);
+      sts32_if(ti == TI0 + jm + 1 && tj == JR, Y + (uint32_t)(j + 1) * 4u, bb);
+      bar_sync_n(bar, 128);
+    }
+#pragma unroll
+    for (int c = JC + 1; c < 16; ++c) {
+      const float l = colval(c);
       const f32x2 l2 = pack2(l, l);
 #pragma unroll
       for (int rp = RP0; rp < 4; ++rp) A[rp][c] = ffma2(w[rp], l2, A[rp][c]);
     }
-    const bool act = (tj > JR) || (tj == JR && ti > TI0 + jm);   // my right-hand-side row ti + 16*tj is below the pivot
-    bb = act ? fmaf(lm * ninv, yj, bb) : bb;
   }
 }
 
