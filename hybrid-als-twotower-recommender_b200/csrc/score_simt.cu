@@ -429,12 +429,20 @@ int score_extrema_simt(const ScoreOperands& O, int64_t n_users, int64_t n_items,
     HALS_LAUNCH_CHECK();
     if (n_items == 0) return 0;
   }
-  const int splits = listed ? (list_splits(n_items) > 1 ? list_splits(n_items) : 2) : score_splits(n_users, n_items);
+  // list mode re-runs a handful of users (typically one or two 64-user tiles): the item range is cut finely enough
+  // to occupy the whole GPU -- extrema combine through order-independent atomic min/max, so splits cost nothing
+  int splits = score_splits(n_users, n_items);
+  if (listed) {
+    const int64_t tiles = (n_items + kScItems - 1) / kScItems;
+    int64_t s = 4 * (int64_t)sm_count();
+    if (s > tiles) s = tiles;
+    splits = (int)(s < 2 ? 2 : s);
+  }
   fill_split(A, n_items, splits);
   const size_t smem = score_smem_bytes(O.ka + O.kt);
   HALS_CUDA(cudaFuncSetAttribute(score_simt_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t gx = (n_users + kScUsers - 1) / kScUsers;
-  if (listed && gx > 32) gx = 32;                 // persistent over the (device-side) list length
+  if (listed && gx > 8) gx = 8;                   // persistent over the (device-side) list length
   dim3 grid((unsigned)gx, (unsigned)splits);
   score_simt_kernel<true, 128><<<grid, kScThreads, smem, st>>>(A, extrema, nullptr, 0.f, 0.f, 0, 0, nullptr,
                                                                  nullptr, nullptr);

@@ -10,7 +10,7 @@ for U in (16384, 65536):
     Ut = torch.nn.functional.layer_norm(torch.randn(U, kt, device="cuda", generator=g), (kt,))
     It = torch.nn.functional.layer_norm(torch.randn(I, kt, device="cuda", generator=g), (kt,))
     sc = scoring.HybridScorer(Ua, Ia, Ut, It)
-    for r in range(2):
+    for r in range(4):
         e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
         e0.record(); ex = sc.extrema(); e1.record(); torch.cuda.synchronize()
         print(U, "extrema ms", e0.elapsed_time(e1), "flagged pass1", sc.flagged_users(U, 0))
