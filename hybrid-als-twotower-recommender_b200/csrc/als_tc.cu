@@ -42,11 +42,9 @@ constexpr int kTcK = 64;
 constexpr int kTcRowBytes = 128;   // one 64-wide bf16 MN atom row
 constexpr int kTcBlk = kTcKC * kTcRowBytes;          // 4096: one [KC][64] block
 constexpr int kTcStageBytes = 3 * kTcBlk;            // H | L | R
-constexpr int kTcLD = kTcK + 1;
 constexpr int kTcLDP = 68;                            // published pivot rows: 16-byte aligned rows (ldlt64_rows)
 constexpr int kTcLDS = 68;                            // accumulator hand-over rows: conflict-free 16-byte stores
 constexpr int kTcSolverBytes = 64 * 68 * 4 + 256 + 256 + 128;   // Pall (every published pivot column) + y, z, x rows
-constexpr int kTcS1Floats = 3 * kTcLDP;              // two pivot-row slots + the x hand-over row
 constexpr int kTcTmemCols = 128;
 constexpr int kTcN = 80;
 

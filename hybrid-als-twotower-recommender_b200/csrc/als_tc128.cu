@@ -34,7 +34,6 @@ constexpr int k8Ahead = 2;
 constexpr int k8Blk = k8KC * 128;           // one [KC][64] bf16 block (4 KB)
 constexpr int k8StageBytes = 5 * k8Blk;     // H0 | H1 | L0 | L1 | R
 constexpr int k8Threads = 320;
-constexpr int k8LDH = 129;                  // leading dimension of the h l^T staging buffer
 constexpr int k8LDP = 132;                  // pivot slot: 128 window floats + rhs (+ pad to 16 B)
 constexpr int k8LDC = 132;                  // row stride of the hand-over matrix C / of Pall (16-byte aligned rows)
 constexpr int k8GroupBytes = 128 * k8LDC * 4 + 4 * 512;        // C (aliased by Pall) + b, y, z, x rows
@@ -382,7 +381,7 @@ als_tc128_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ v
                  const int32_t* __restrict__ item_row, const int64_t* __restrict__ item_begin,
                  const int32_t* __restrict__ item_len, const int32_t* __restrict__ item_slot,
                  int64_t n_items, float* __restrict__ workspace) {
-  constexpr int K = k8K, KC = k8KC;
+  constexpr int K = k8K;
   extern __shared__ uint8_t smem_dyn[];
   __shared__ uint64_t mbar_free[k8Stages];
   __shared__ uint64_t mbar_acc[2];        // accumulator complete, one per solver group

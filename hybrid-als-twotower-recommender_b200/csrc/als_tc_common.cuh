@@ -33,8 +33,8 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
   asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
-__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;\n" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;\n" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ float lo2(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi2(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
 __device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {   // a * b + c, both halves
   f32x2 d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(a), "l"(b), "l"(c));

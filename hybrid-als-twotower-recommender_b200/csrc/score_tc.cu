@@ -534,7 +534,6 @@ __global__ void score_select_kernel(int stride /* key slots per stream */, uint6
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (int64_t)n_splits * n_users) return;
-  const int64_t u = row % n_users;
   uint64_t* buf = cand + (size_t)row * stride;
   uint64_t tkey;
   const int have = cand_cnt[row] < CAP ? cand_cnt[row] : CAP;   // surplus keys (score ties at the trim threshold) count as rejected
