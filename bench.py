@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=25_000_000, help="ratings per half-step in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel / collective individually in the timed sweeps")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     ap.add_argument("--no-scoring", action="store_true", help="skip the hybrid top-k scoring leg (extra.hybrid_topk)")
     ap.add_argument("--score-users", type=int, default=65536)
@@ -298,6 +299,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphs_on = (not args.no_graphs) and eng.enable_graphs()
     for _ in range(max(args.warmup, 3)):
         eng.sweep()
     barrier()
@@ -306,6 +308,7 @@ def main():
         sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     l0 = nat.launch_count()
+    g0 = eng.graph_launches
     barrier()
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -314,7 +317,7 @@ def main():
         ev[s][2].record(); eng.user_half_step(); ev[s][3].record()
     t_end.record()
     barrier()
-    launches = nat.launch_count() - l0
+    launches = nat.launch_count() - l0 + (eng.graph_launches - g0)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = t_start.elapsed_time(t_end)
     t_item = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
@@ -377,7 +380,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "step": "one ALS sweep = item half-step + user half-step "
-                   "(+ factor all-gathers when sharded)", "rows": "nnz-balanced contiguous row shards per rank",
+                   "(+ factor all-gathers when sharded)", "launch": "one CUDA graph per half-step" if graphs_on else "plain launches", "rows": "nnz-balanced contiguous row shards per rank",
                    "l2": "per-step inputs (2 CSR orientations + factors) exceed the 126 MB L2; no flush between steps",
                    "train_rmse_after_run": rmse_train},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(w["nnz"] * 12),

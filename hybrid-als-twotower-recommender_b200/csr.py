@@ -79,8 +79,31 @@ class AlsPlanHandle:
     def __init__(self, shard: CsrShard, k: int, seg_len: int | None = None, device=None, n_src: int = 0):
         L = nat.lib()
         self.k = k
-        self.seg_len = int(seg_len or L.hals_als_default_seg_len(k))
         rp = np.ascontiguousarray(shard.rowptr_host, dtype=np.int64)
+        if seg_len:
+            self.seg_len = int(seg_len)
+        else:
+            # Long rows are cut into slices of at most seg_len ratings; slices are what the persistent CTAs
+            # round-robin over.  A small shard (one of 8 ranks on the MovieLens-20M shape) with the default 4096
+            # would hand each CTA one or two slices and lose up to a slice time to quantisation, so the slice
+            # shrinks until a CTA sees ~8 of them (bounded below: every slice costs a workspace slot).
+            default = int(L.hals_als_default_seg_len(k))
+            ctas = 4 * 148
+            dev0 = torch.device(device) if device is not None else shard.colidx.device
+            if dev0.type == "cuda":
+                ctas = 4 * torch.cuda.get_device_properties(dev0).multi_processor_count
+            lens = np.diff(rp)
+            nnz = int(rp[-1])
+            want = nnz // (8 * ctas) // 32 * 32
+            # only shards whose ratings sit mostly in long rows (a Zipf head of items) are made of slices; where
+            # long rows are the exception (users) finer slices just add slot traffic (measured: slower)
+            heavy = nnz > 0 and float(lens[lens > default].sum()) > 0.25 * nnz
+            seg = max(512, min(default, want)) if (want > 0 and heavy) else default
+            # ... but every sliced row goes through the slot reduction (one small CTA per row): shrinking must not
+            # turn thousands of mid-sized rows (active users) into long rows
+            while seg < default and int((lens > seg).sum()) > 2 * ctas:
+                seg = min(default, seg * 2)
+            self.seg_len = seg
         m = len(rp) - 1
         n_items, n_long, n_slots = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         nat.check(L.hals_als_plan_count_host(nat.ptr(rp), m, self.seg_len, ctypes.byref(n_items),
