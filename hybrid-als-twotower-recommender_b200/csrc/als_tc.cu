@@ -550,19 +550,26 @@ als_tc64_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ va
 // are summed (fixed order) into the group's first slot; a Zipf-head row with hundreds of slices would otherwise
 // be summed by a single CTA.  grid = (n_long_rows, ceil(max_nseg / kSlotGroup)).
 constexpr int kSlotGroup = 16;
+// `stride` = distance between the partial sums of this level (1: raw slots, 16: the level-1 group leaders).
 __global__ void __launch_bounds__(256)
 als_slot_group_sum_kernel(float* __restrict__ workspace, const int32_t* __restrict__ long_slot0,
-                          const int32_t* __restrict__ long_nseg, int slot_floats) {
+                          const int32_t* __restrict__ long_nseg, int slot_floats, int stride) {
   const int ns = long_nseg[blockIdx.x];
-  const int g0 = blockIdx.y * kSlotGroup;
-  if (g0 >= ns || ns <= kSlotGroup) return;            // short lists are summed by the solve kernel directly
-  const int g1 = min(ns, g0 + kSlotGroup);
+  const int span = kSlotGroup * stride;                 // slots covered by one group of this level
+  const int g0 = blockIdx.y * span;
+  if (g0 >= ns || ns <= stride * kSlotGroup) return;    // this row does not need this level
+  const int g1 = min(ns, g0 + span);
   float* base = workspace + (size_t)(long_slot0[blockIdx.x] + g0) * slot_floats;
   for (int e = threadIdx.x; e < slot_floats; e += 256) {
     float s = base[e];
-    for (int q = 1; q < g1 - g0; ++q) s += base[(size_t)q * slot_floats + e];
+    for (int q = stride; q < g1 - g0; q += stride) s += base[(size_t)q * slot_floats + e];
     base[e] = s;
   }
+}
+
+// distance between the partial sums the solve kernels still have to add for a row of ns slices
+__host__ __device__ inline int slot_final_stride(int ns) {
+  return ns > kSlotGroup * kSlotGroup ? kSlotGroup * kSlotGroup : ns > kSlotGroup ? kSlotGroup : 1;
 }
 
 // Long rows (rank 64): sums the per-slice partial (A, b, n) slots in slot order -- deterministic -- adds the
@@ -581,7 +588,7 @@ als_reduce_solve64_kernel(const float* __restrict__ workspace, float* __restrict
 #pragma unroll
   for (int n = 0; n < 65; ++n) a[n] = 0.f;
   float cnt = 0.f;
-  const int stride = ns > kSlotGroup ? kSlotGroup : 1;  // rows with many slices were pre-summed per group
+  const int stride = slot_final_stride(ns);             // rows with many slices were pre-summed per group (two levels)
   for (int q = 0; q < ns; q += stride) {
     const float* W = workspace + (size_t)(s0 + q) * sf;
 #pragma unroll
@@ -602,9 +609,12 @@ als_reduce_solve64_kernel(const float* __restrict__ workspace, float* __restrict
 }
 
 int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_floats, cudaStream_t st) {
-  if (plan->max_nseg > kSlotGroup) {
-    dim3 g((unsigned)plan->n_long_rows, (unsigned)((plan->max_nseg + kSlotGroup - 1) / kSlotGroup));
-    als_slot_group_sum_kernel<<<g, 256, 0, st>>>(slots, plan->long_slot0, plan->long_nseg, slot_floats);
+  // level 1: groups of 16 slices; level 2 (rows with more than 256 slices): groups of 16 level-1 leaders
+  for (int stride = 1; stride <= kSlotGroup; stride *= kSlotGroup) {
+    if (plan->max_nseg <= stride * kSlotGroup) break;
+    const int span = stride * kSlotGroup;
+    dim3 g((unsigned)plan->n_long_rows, (unsigned)((plan->max_nseg + span - 1) / span));
+    als_slot_group_sum_kernel<<<g, 256, 0, st>>>(slots, plan->long_slot0, plan->long_nseg, slot_floats, stride);
     HALS_LAUNCH_CHECK();
   }
   return 0;

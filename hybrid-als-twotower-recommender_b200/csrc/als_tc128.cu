@@ -483,7 +483,7 @@ als_reduce_solve128_kernel(const float* __restrict__ workspace, float* __restric
 #pragma unroll
   for (int n = 0; n < 128; ++n) a[n] = 0.f;
   float bm = 0.f, cnt = 0.f;
-  const int stride = ns > slot_group ? slot_group : 1;
+  const int stride = ns > slot_group * slot_group ? slot_group * slot_group : ns > slot_group ? slot_group : 1;   // two pre-sum levels
   for (int q = 0; q < ns; q += stride) {
     const float* W = workspace + (size_t)(s0 + q) * k8SlotFloats;
 #pragma unroll

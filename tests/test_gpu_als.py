@@ -103,6 +103,20 @@ def test_long_rows_are_sliced_deterministically(k, seg):
     assert np.array_equal(got, again), "bitwise reproducible (no float atomics)"
 
 
+@pytest.mark.parametrize("k", [64, 128])
+def test_many_slices_use_the_two_level_slot_reduction(k):
+    """A row cut into more than 256 slices (seg_len 32): slot sums go through both pre-sum levels."""
+    U, I, nnz = 4000, 6, 60000             # ~10k ratings per item row -> ~310 slices each
+    u, i, r = synth(U, I, nnz, 11, skew=False)
+    X = als_oracle.init_factors(U, k, 3)
+    got, plan = gpu_half_step(i, u, r, I, X, 0.1, seg_len=32)
+    assert plan.n_long > 0 and int(plan.host["long_nseg"][: plan.n_long].max()) > 256
+    rp, ci, v = als_oracle.coo_to_csr(i, u, r, I)
+    assert_close(got, c_oracle.als_half_step(rp, ci, v, X, 0.1))
+    again, _ = gpu_half_step(i, u, r, I, X, 0.1, seg_len=32)
+    assert np.array_equal(got, again)
+
+
 def test_empty_rows_duplicates_and_single_rating():
     k = 10
     X = als_oracle.init_factors(50, k, 0)
