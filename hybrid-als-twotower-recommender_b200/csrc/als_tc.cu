@@ -29,7 +29,10 @@
 namespace hals {
 
 constexpr int kTcThreads = 128;
-constexpr int kTcKC = 32;          // ratings per stage
+#ifndef HALS_TC_KC
+#define HALS_TC_KC 32
+#endif
+constexpr int kTcKC = HALS_TC_KC;  // ratings per stage (16 or 32)
 #ifndef HALS_TC_STAGES
 #define HALS_TC_STAGES 3
 #endif
@@ -424,7 +427,7 @@ als_tc64_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ va
       // chunk ahead of its use so the dependent gather never waits on the index load
       auto fetch_idx = [&](int c, int& ci, float& rv) {
         const int q = c * KC + lane;
-        const bool ok = q < len;
+        const bool ok = lane < KC && q < len;
         ci = ok ? __ldg(colidx + begin + q) : -1;
         rv = (ok && ptid < 32) ? __ldg(vals + begin + q) : 0.f;
       };
@@ -446,7 +449,7 @@ als_tc64_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ va
           cp_async16(st + blk_off + t * kTcRowBytes + ((chunk ^ (t & 7)) << 4),
                      reinterpret_cast<const uint8_t*>(src_hl) + (size_t)(ci < 0 ? 0 : ci) * (4 * K) + piece * 16, ci >= 0);
         }
-        if (ptid < 32) {    // rating columns of the B operand: element 0 = bf16(r), element 1 = bf16(r - bf16(r))
+        if (ptid < KC) {    // rating columns of the B operand: element 0 = bf16(r), element 1 = bf16(r - bf16(r))
           const __nv_bfloat16 rh = __float2bfloat16_rn(rv_cur);
           const __nv_bfloat16 rl = __float2bfloat16_rn(rv_cur - __bfloat162float(rh));
           const uint32_t packed = (uint32_t)__bfloat16_as_ushort(rh) | ((uint32_t)__bfloat16_as_ushort(rl) << 16);
