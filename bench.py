@@ -201,6 +201,30 @@ def run_reference(args, w):
     print(json.dumps(line))
 
 
+def scoring_cpu_baseline(Ua, Ia, Ut, It, k, n_users=128):
+    """Restated CPU baseline of the scoring path on the host cores: torch-CPU fp32 matmul of both
+    models over a slice of users, per-user min-max, 0.8/0.2 blend, top-k.  The reference itself loops over users in
+    Python around Keras predict + sklearn + sorted(); TensorFlow is not in the image, so this is the generous form."""
+    import torch
+    n = min(n_users, Ua.shape[0])
+    ua, ut, ia, it = Ua[:n].cpu(), Ut[:n].cpu(), Ia.cpu(), It.cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def once():
+        sa, st = ua @ ia.T, ut @ it.T
+        na = (sa - sa.amin(1, keepdim=True)) / (sa.amax(1, keepdim=True) - sa.amin(1, keepdim=True)).clamp_min(1e-30)
+        nt = (st - st.amin(1, keepdim=True)) / (st.amax(1, keepdim=True) - st.amin(1, keepdim=True)).clamp_min(1e-30)
+        return torch.topk(0.8 * na + 0.2 * nt, k, dim=1)
+
+    once()
+    t0 = time.perf_counter()
+    once()
+    dt = time.perf_counter() - t0
+    return {"value": n * float(Ia.shape[0]) / dt, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} users x {Ia.shape[0]} items in {dt:.2f}s: torch-CPU fp32 matmul (128-d + 50-d), per-user "
+                      "min-max, 0.8/0.2 blend, topk; TF/Keras unavailable offline"}
+
+
 def scoring_leg(args, dev, rank, world, barrier):
     """Second headline metric: hybrid scored user-item pairs/s (BASELINE config 5 shape, item-sharded:
     every rank holds 1.25M items -- 10M at 8 GPUs -- and a slice of the 1M users).  Two fused passes
@@ -238,7 +262,11 @@ def scoring_leg(args, dev, rank, world, barrier):
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
     except Exception:
         peak = 1590.0
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = scoring_cpu_baseline(Ua, Ia, Ut, It, k)
     return {"metric": "hybrid_scored_pairs_per_sec", "value": pairs / ((t1 + t2) * 1e-3), "unit": "pairs/s",
+            "cpu_baseline": cpu,
             "config": {"users": U, "items_per_gpu": I, "items_total": I * world, "k_als": ka, "k_tower": kt, "topk": k,
                        "weights": [0.8, 0.2], "sharding": "item-sharded, users replicated"},
             "ms_extrema_pass": t1, "ms_blend_topk_pass": t2,
