@@ -16,8 +16,10 @@
 // Data movement: the h|l rows (256 B, contiguous) are gathered global->shared with cp.async
 // straight into the 128B-swizzled MN-major layout the UMMA descriptors expect (layout pinned by
 // tests/test_gpu_umma.py); 3-stage ring, stages recycled through tcgen05.commit -> mbarrier.
-// Persistent CTAs (4 per SM: 128 TMEM columns each), static round-robin over work items, so
-// while one CTA factorises a row (CUDA cores) the others keep the gather/tensor pipes busy.
+// Persistent CTAs (4 per SM: 128 TMEM columns each), static round-robin over work items; inside a CTA two
+// producer warps gather + issue the MMAs of the next work item while two solver warps factorise the current one
+// (als64_solve_tile: 2-D cyclic register tiling of the 64 x 64 system, see below).  ldlt64_rows (thread = matrix
+// row) is the earlier solver; the long-row reduce kernel still uses it.
 #include <cuda_bf16.h>
 
 #include <cstdlib>

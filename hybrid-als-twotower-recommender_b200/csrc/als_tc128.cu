@@ -11,12 +11,12 @@
 //
 // One persistent CTA per SM (the accumulator needs 288 of the 512 TMEM columns), 10 warps:
 //   warps 0,1   producers: cp.async gather into the swizzled MN-major stage ring, one thread issues the MMAs
-//   warps 2-5   solver group A, warps 6-9 solver group B: thread = matrix row = TMEM lane; the groups take
-//               alternate work items, so while one group eliminates (128 dependent pivot steps) the other
-//               drains / eliminates the next row and the producers gather the one after.
-// The elimination is ldlt64_rows' scheme at twice the width: rotating register window (4 pivots per loop
-// iteration), pivot row published to a 2-slot shared buffer, one named barrier per step whose participant
-// count shrinks as warps run out of rows (128 / 96 / 64 threads, then __syncwarp).
+//   warps 2-5   solver group A, warps 6-9 solver group B: the groups take alternate work items, so while one
+//               group eliminates (128 dependent pivot steps) the other drains / eliminates the next row and the
+//               producers gather the one after.  A group drains row m of C = D_hh/2 + D_hl per thread (thread =
+//               TMEM lane), then solves with the 2-D cyclic register tiling (als128_solve_tile, 16 x 8 thread grid).
+// ldlt128_rows (thread = matrix row, rotating register window, 2-slot pivot buffer, shrinking named barriers) is the
+// earlier solver; the long-row reduce kernel still uses it.
 #include <cuda_bf16.h>
 
 #include <cstdlib>
