@@ -17,12 +17,13 @@
 // eps_u), i.e. no rejected item could belong to the answer; otherwise the user is flagged and
 // re-done by the exact SIMT kernel (score_simt.cu) -- on the GPU, never on the host.
 //
-// Kernel shape: CTA = 128 users (UMMA M) x a contiguous item range, 6 warps:
-//   warp 0   TMA producer: user tile once, item K-blocks ([BN x 64] bf16, 128B swizzle) through a
-//            4-stage ring
-//   warp 1   MMA issuer: 4 x tcgen05.mma (K=16) per K-block, accumulators double-buffered in TMEM
-//            (pass 2: 2 x 256 columns; pass 1: 2 x (128 + 128) columns for the two models)
-//   warps 2-5 epilogue: tcgen05.ld 32 columns at a time, thread = user row, register threshold.
+// Kernel shape: CTA = 128 users (UMMA M) x a contiguous item range, 10 warps:
+//   warp 0    TMA producer: user tile once, item K-blocks ([256 x 64] bf16, 128B swizzle) through a 4-stage ring
+//   warp 1    MMA issuer: 4 x tcgen05.mma (M=128, N=256, K=16) per K-block, accumulators double-buffered in TMEM
+//             (2 x 256 columns; pass 1 scores the two models as two consecutive accumulator jobs per item tile)
+//   warps 2-9 epilogue, two warps per TMEM lane quarter (each takes half of the tile's columns): tcgen05.ld 32 / 64
+//             columns per step with the next load in flight, thread = user row, FMNMX3 chains per 8-column octet
+//             against the row threshold held in a register; only octets with a survivor walk their columns.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
