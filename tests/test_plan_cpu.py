@@ -1,0 +1,54 @@
+"""Host-side work-plan logic (no GPU): slice-length choice of AlsPlanHandle and plan consistency.
+
+The plan stands where Spark cuts ratings into in-blocks (ALS.scala makeBlocks, reached from
+src/als_model.py:62); the kernels only ever see its arrays."""
+import numpy as np
+import torch
+
+from hybrid_als_twotower_recommender_b200 import _native as nat
+from hybrid_als_twotower_recommender_b200.csr import AlsPlanHandle, CsrShard
+
+
+def _shard(lens):
+    lens = np.asarray(lens, dtype=np.int64)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    nnz = int(rp[-1])
+    return CsrShard(0, len(lens), len(lens), torch.from_numpy(rp.copy()), torch.zeros(nnz, dtype=torch.int32),
+                    torch.zeros(nnz, dtype=torch.float32), rp)
+
+
+def _check_plan(plan, lens):
+    h, n = plan.host, plan.n_items
+    covered = np.zeros(len(lens), dtype=np.int64)
+    np.add.at(covered, h["item_row"][:n], h["item_len"][:n])
+    assert np.array_equal(covered, np.asarray(lens)[: len(covered)] * (np.asarray(lens) > 0))   # every rating exactly once
+    assert h["item_len"][:n].max() <= plan.seg_len
+    sliced = h["item_slot"][:n] >= 0
+    assert int(sliced.sum()) == plan.n_slots
+    assert plan.n_long == len(set(h["item_row"][:n][sliced].tolist()))
+
+
+def test_default_slice_length_for_light_rows():
+    lens = np.full(20000, 150)                       # user-like shard: no heavy rows -> no reason to slice finer
+    default = int(nat.lib().hals_als_default_seg_len(64))
+    plan = AlsPlanHandle(_shard(lens), 64, device="cpu")
+    assert plan.seg_len == default and plan.n_long == 0
+    _check_plan(plan, lens)
+
+
+def test_small_heavy_tailed_shard_gets_finer_slices():
+    lens = np.concatenate([[900_000, 300_000, 120_000], np.full(3000, 200)])   # one rank's share of a Zipf head
+    default = int(nat.lib().hals_als_default_seg_len(64))
+    plan = AlsPlanHandle(_shard(lens), 64, device="cpu")
+    assert 512 <= plan.seg_len < default and plan.seg_len % 32 == 0
+    assert plan.n_long >= 3
+    _check_plan(plan, lens)
+
+
+def test_big_shard_keeps_the_default_and_explicit_value_wins():
+    lens = np.concatenate([[1_800_000, 900_000], np.full(26000, 650)])        # ~20M ratings: already ~8 slices per CTA
+    default = int(nat.lib().hals_als_default_seg_len(64))
+    assert AlsPlanHandle(_shard(lens), 64, device="cpu").seg_len == default
+    plan = AlsPlanHandle(_shard([5000, 10, 0, 70]), 64, seg_len=64, device="cpu")
+    assert plan.seg_len == 64 and plan.n_long == 2
+    _check_plan(plan, [5000, 10, 0, 70])
