@@ -60,7 +60,7 @@ __global__ void score_prep_kernel(const float* __restrict__ A, int64_t a_stride,
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
-  const int Kp = 64 * (nkb_a + nkb_t);
+  const int Kp = 64 * (nkb_a + nkb_t), Ka = 64 * nkb_a;
   float sa = 1.f, st = 1.f;
   if (extrema != nullptr) {   // user side of pass 2: fold alpha = w/range (zero range contributes nothing)
     const float4 ex = reinterpret_cast<const float4*>(extrema)[row];
@@ -69,18 +69,31 @@ __global__ void score_prep_kernel(const float* __restrict__ A, int64_t a_stride,
     st = (rt != 0.f) ? w_tt / rt : 0.f;
   }
   float na = 0.f, nt = 0.f;
-  __nv_bfloat16* o = out + row * Kp;
-  for (int f = lane; f < Kp; f += 32) {
-    float v = 0.f;
-    if (f < 64 * nkb_a) {
-      if (f < ka) v = A[row * a_stride + f] * sa;
-      na = fmaf(v, v, na);
+  // each lane converts 8 consecutive outputs and writes them with one 16-byte store (Kp / 8 <= 32 chunks per row)
+  const int f0 = lane * 8;
+  if (f0 < Kp) {
+    const bool is_a = f0 < Ka;                          // a chunk never straddles the two parts (Ka is a multiple of 64)
+    const float* src = is_a ? A + row * a_stride : T + row * t_stride;
+    const int g0 = is_a ? f0 : f0 - Ka, kk = is_a ? ka : kt;
+    const float sc = is_a ? sa : st;
+    float v[8];
+    if (g0 + 8 <= kk && ((reinterpret_cast<uintptr_t>(src + g0) & 15) == 0)) {
+      const float4 p = *reinterpret_cast<const float4*>(src + g0), q = *reinterpret_cast<const float4*>(src + g0 + 4);
+      v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
     } else {
-      const int g = f - 64 * nkb_a;
-      if (g < kt) v = T[row * t_stride + g] * st;
-      nt = fmaf(v, v, nt);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (g0 + i < kk) ? src[g0 + i] : 0.f;
     }
-    o[f] = __float2bfloat16_rn(v);
+    float s2 = 0.f;
+    __align__(16) __nv_bfloat16 o8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] *= sc;
+      s2 = fmaf(v[i], v[i], s2);
+      o8[i] = __float2bfloat16_rn(v[i]);
+    }
+    if (is_a) na = s2; else nt = s2;
+    *reinterpret_cast<uint4*>(out + row * Kp + f0) = *reinterpret_cast<const uint4*>(o8);
   }
   na = sqrtf(warp_sum(na));
   nt = sqrtf(warp_sum(nt));
