@@ -73,6 +73,8 @@ extern "C" int hals_als_plan_fill_host(const int64_t* rowptr_host, int64_t m, in
   HALS_REQUIRE(seg_len >= 32, "seg_len must be >= 32");
   struct Item { int32_t row; int64_t begin; int32_t len; int32_t slot; };
   std::vector<Item> segs, rows;
+  rows.reserve((size_t)m);
+  segs.reserve((size_t)(rowptr_host[m] / seg_len + 16));
   int64_t lr = 0, slot = 0;
   for (int64_t j = 0; j < m; ++j) {
     const int64_t b = rowptr_host[j], len = rowptr_host[j + 1] - b;
