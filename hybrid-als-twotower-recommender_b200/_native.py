@@ -28,6 +28,8 @@ class AlsPlan(ctypes.Structure):
         ("seg_len", c_i32), ("max_nseg", c_i32),
         ("item_row", c_vp), ("item_begin", c_vp), ("item_len", c_vp), ("item_slot", c_vp),
         ("long_row", c_vp), ("long_slot0", c_vp), ("long_nseg", c_vp),
+        ("n_chunks", c_i64), ("item_chunk0", c_vp), ("item_cost0", c_vp), ("chunk_pos", c_vp), ("chunk_cnt", c_vp),
+        ("vals_hl", c_vp),
     ]
 
 
@@ -50,8 +52,11 @@ SIGNATURES = {
     "hals_max_rank": (ctypes.c_int, []),
     "hals_als_plan_count_host": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "hals_als_plan_fill_host": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hals_als_plan_chunk_count_host": (c_i64, [c_vp, c_i64]),
+    "hals_als_plan_chunks_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "hals_als_workspace_bytes": (c_sz, [c_i64, ctypes.c_int, c_i64]),
     "hals_als_default_seg_len": (c_i32, [ctypes.c_int]),
+    "hals_als_pack_ratings": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
     "hals_als_half_step": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, ctypes.c_int, c_f32,
                                           ctypes.c_int, c_f32, c_vp, ctypes.POINTER(AlsPlan), c_vp, c_sz, c_vp]),
     "hals_gram_workspace_bytes": (c_sz, [ctypes.c_int]),

@@ -120,12 +120,30 @@ class AlsPlanHandle:
         }
         nat.check(L.hals_als_plan_fill_host(nat.ptr(rp), m, self.seg_len, *(nat.ptr(h[n]) for n in (
             "item_row", "item_begin", "item_len", "item_slot", "long_row", "long_slot0", "long_nseg"))), "plan_fill")
+        # chunk table (pieces of 32 ratings) + cost prefix: what the persistent rank-64 kernel streams
+        self.n_chunks = 0
+        if k == 64 and self.n_items > 0:
+            self.n_chunks = int(L.hals_als_plan_chunk_count_host(nat.ptr(h["item_len"]), self.n_items))
+            h["item_chunk0"] = np.empty(self.n_items + 1, np.int64)
+            h["item_cost0"] = np.empty(self.n_items + 1, np.int64)
+            h["chunk_pos"] = np.empty(max(self.n_chunks, 1), np.int64)
+            h["chunk_cnt"] = np.empty(max(self.n_chunks, 1), np.int32)
+            nat.check(L.hals_als_plan_chunks_host(nat.ptr(h["item_len"]), nat.ptr(h["item_begin"]), nat.ptr(h["item_slot"]),
+                                                  self.n_items, nat.ptr(h["item_chunk0"]), nat.ptr(h["item_cost0"]),
+                                                  nat.ptr(h["chunk_pos"]), nat.ptr(h["chunk_cnt"])), "plan_chunks")
         self.host = h
         dev = device if device is not None else shard.colidx.device
         self.dev = {n: torch.from_numpy(a).to(dev) for n, a in h.items()}
+        # ratings as bf16 hi|lo pairs, packed once: the rank-64 tensor-core kernel copies them into its operand
+        self.vals_hl = None
+        if k == 64 and torch.device(dev).type == "cuda" and shard.vals.numel() > 0:
+            self.vals_hl = torch.empty(shard.vals.numel(), dtype=torch.int32, device=dev)
+            nat.check(L.hals_als_pack_ratings(nat.ptr(shard.vals), shard.vals.numel(), nat.ptr(self.vals_hl),
+                                              nat.current_stream()), "hals_als_pack_ratings")
         self.struct = nat.AlsPlan(
             n_items=self.n_items, n_long_rows=self.n_long, n_slots=self.n_slots, seg_len=self.seg_len,
             max_nseg=int(h["long_nseg"][: self.n_long].max()) if self.n_long else 0,
+            vals_hl=self.vals_hl.data_ptr() if self.vals_hl is not None else None, n_chunks=self.n_chunks,
             **{n: self.dev[n].data_ptr() for n in h})
         self.workspace_bytes = int(L.hals_als_workspace_bytes(self.n_slots, k, int(n_src)))
         self.workspace = torch.empty(max(self.workspace_bytes, 16), dtype=torch.uint8, device=dev)

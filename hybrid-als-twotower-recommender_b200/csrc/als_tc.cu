@@ -625,6 +625,13 @@ int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_
   return 0;
 }
 
+int als_launch_reduce_solve64(const float* slots, float* dst, float reg, const hals_als_plan* plan, cudaStream_t st) {
+  als_reduce_solve64_kernel<<<(unsigned)plan->n_long_rows, 64, 0, st>>>(slots, dst, reg, plan->long_row, plan->long_slot0,
+                                                                        plan->long_nseg);
+  HALS_LAUNCH_CHECK();
+  return 0;
+}
+
 int als_launch_split_bf16(const float* src, int64_t n_src, int k, void* out, cudaStream_t st) {
   const int64_t nthreads = n_src * (k / 8);
   split_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(src, n_src, k, reinterpret_cast<__nv_bfloat16*>(out));

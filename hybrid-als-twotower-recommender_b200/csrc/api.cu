@@ -15,6 +15,9 @@ int als_half_step_tc128(const int32_t* colidx, const float* vals, const float* s
                         float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
 int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* src, int64_t n_src, float* dst,
                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
+int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const float* src, int64_t n_src, float* dst,
+                       float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
+int als_pack_ratings(const float* vals, int64_t nnz, uint32_t* out, cudaStream_t st);
 }  // namespace hals
 
 using namespace hals;
@@ -40,7 +43,7 @@ static bool use_tc(int k, int implicit) {
 
 extern "C" size_t hals_als_workspace_bytes(int64_t n_slots, int k, int64_t n_src) {
   // [partial (A,b,n) slots][bf16 h|l split of the source factors, tensor-core path]
-  return slot_region_bytes(n_slots, k) + (size_t)(n_src > 0 ? n_src : 0) * 4 * (size_t)k + 256;
+  return slot_region_bytes(n_slots, k) + (size_t)(n_src > 0 ? n_src : 0) * 4 * (size_t)k + 1024;   // + one all-zero row
 }
 
 // Work items: first every slice of every long row (big, uniform items first so that the
@@ -92,22 +95,58 @@ extern "C" int hals_als_plan_fill_host(const int64_t* rowptr_host, int64_t m, in
       ++slot;
     }
   }
-  // Emission order.  The kernels walk the items round-robin over a persistent grid (4 CTAs x 148 SMs): a block of
-  // kPlanBlock slices (gather-heavy, nothing to solve) is followed by its share of whole rows (solve-heavy), so
-  // that every CTA alternates between the two and its solver warps work while its producers gather a slice.
-  // With fewer than one block of slices this degenerates to "slices first, then rows".
-  constexpr int64_t kPlanBlock = 592;
-  const int64_t nblk = segs.empty() ? 1 : ((int64_t)segs.size() + kPlanBlock - 1) / kPlanBlock;
-  const int64_t rows_per_blk = ((int64_t)rows.size() + nblk - 1) / nblk;
-  int64_t it = 0;
+  // Emission order: slices (gather-heavy, nothing to solve) are spread evenly among the whole rows (solve-heavy), so
+  // that any contiguous run of items -- the persistent kernels take contiguous or round-robin shares of this list --
+  // mixes the two in the global proportion and the gather and solve pipes of an SM both stay busy.
+  const int64_t S = (int64_t)segs.size(), R = (int64_t)rows.size();
+  int64_t it = 0, si = 0, ri = 0;
   auto emit = [&](const Item& x) {
     item_row[it] = x.row; item_begin[it] = x.begin; item_len[it] = x.len; item_slot[it] = x.slot; ++it;
   };
-  for (int64_t b = 0; b < nblk; ++b) {
-    for (int64_t s = b * kPlanBlock; s < (b + 1) * kPlanBlock && s < (int64_t)segs.size(); ++s) emit(segs[s]);
-    for (int64_t r = b * rows_per_blk; r < (b + 1) * rows_per_blk && r < (int64_t)rows.size(); ++r) emit(rows[r]);
+  while (si < S || ri < R) {
+    // progress fractions (si + 1/2) / S vs (ri + 1/2) / R, compared without division
+    const bool take_slice = si < S && (ri >= R || (2 * si + 1) * R <= (2 * ri + 1) * S);
+    if (take_slice) emit(segs[si++]); else emit(rows[ri++]);
   }
   return 0;
+}
+
+extern "C" int64_t hals_als_plan_chunk_count_host(const int32_t* item_len, int64_t n_items) {
+  if (!item_len || n_items < 0) return -1;
+  int64_t n = 0;
+  for (int64_t i = 0; i < n_items; ++i) {
+    if (item_len[i] <= 0) return -1;
+    n += (item_len[i] + 31) / 32;
+  }
+  return n;
+}
+
+extern "C" int hals_als_plan_chunks_host(const int32_t* item_len, const int64_t* item_begin, const int32_t* item_slot,
+                                         int64_t n_items, int64_t* item_chunk0, int64_t* item_cost0, int64_t* chunk_pos,
+                                         int32_t* chunk_cnt) {
+  HALS_REQUIRE(item_len && item_begin && item_slot && item_chunk0 && item_cost0 && chunk_pos && chunk_cnt, "null pointer");
+  // cost of an item in chunk units: its chunks + the solve of a whole row (measured ~6 chunk times with the solvers
+  // of an SM working in parallel) or the parking of a slice's partial sums
+  constexpr int64_t kSolveCost = 6, kParkCost = 2;
+  int64_t c = 0, cost = 0;
+  for (int64_t i = 0; i < n_items; ++i) {
+    item_chunk0[i] = c;
+    item_cost0[i] = cost;
+    const int32_t len = item_len[i];
+    HALS_REQUIRE(len > 0, "empty work item");
+    for (int32_t o = 0; o < len; o += 32) { chunk_pos[c] = item_begin[i] + o; chunk_cnt[c] = len - o; ++c; }
+    cost += (len + 31) / 32 + (item_slot[i] < 0 ? kSolveCost : kParkCost);
+  }
+  item_chunk0[n_items] = c;
+  item_cost0[n_items] = cost;
+  return 0;
+}
+
+extern "C" int hals_als_pack_ratings(const float* vals, int64_t nnz, uint32_t* out, void* stream) {
+  HALS_REQUIRE(nnz >= 0, "negative count");
+  if (nnz == 0) return 0;
+  HALS_REQUIRE(vals && out, "null pointer");
+  return als_pack_ratings(vals, nnz, out, (cudaStream_t)stream);
 }
 
 extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, const float* vals,
@@ -135,7 +174,11 @@ extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, 
   if (use_tc(k, implicit)) {
     void* split = reinterpret_cast<uint8_t*>(workspace) + slot_region_bytes(plan->n_slots, k);
     if (k == 128) return als_half_step_tc128(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
-    return als_half_step_tc64(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
+    // HALS_TC64_IMPL=cta4 selects the round-1 kernel (four 4-warp CTAs per SM); default: warp-specialised kernel
+    static const bool old64 = [] { const char* e = getenv("HALS_TC64_IMPL"); return e && e[0] == 'c'; }();
+    if (old64 || plan->vals_hl == nullptr || plan->chunk_pos == nullptr)
+      return als_half_step_tc64(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
+    return als_half_step_ws64(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split, st);
   }
   return als_half_step_simt(colidx, vals, src, dst, k, reg, implicit, alpha, gram, plan, (float*)workspace, st);
 }

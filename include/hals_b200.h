@@ -72,6 +72,18 @@ typedef struct hals_als_plan {
   const int32_t* long_row;   /* [n_long_rows] destination row                              */
   const int32_t* long_slot0; /* [n_long_rows] first slot                                   */
   const int32_t* long_nseg;  /* [n_long_rows] number of slots                              */
+  /* Chunk table (optional; hals_als_plan_chunks_host).  The ratings of work item i, cut into pieces of 32, are chunks
+   * [item_chunk0[i], item_chunk0[i+1]); the persistent rank-64 kernel gives every CTA a CONTIGUOUS range of items of
+   * equal cost (item_cost0 = prefix sum of chunks + a per-item solve / park cost) and streams its chunks. */
+  int64_t n_chunks;
+  const int64_t* item_chunk0; /* [n_items+1] */
+  const int64_t* item_cost0;  /* [n_items+1] */
+  const int64_t* chunk_pos;   /* [n_chunks] index of the chunk's first rating (into colidx / vals)              */
+  const int32_t* chunk_cnt;   /* [n_chunks] ratings left in its item at that point (<= 32: the item's last chunk) */
+  const uint32_t* vals_hl;   /* optional [nnz], same order as vals: bf16(r) | bf16(r - bf16(r)) << 16, written by
+                                hals_als_pack_ratings once per ratings matrix.  The rank-64 tensor-core kernel
+                                copies it straight into the MMA operand; NULL selects the slower kernel that
+                                converts the fp32 ratings itself. */
 } hals_als_plan;
 
 /* Host-side planner (pure CPU, no CUDA): sizes first, then fill caller arrays.
@@ -82,11 +94,19 @@ int hals_als_plan_fill_host(const int64_t* rowptr_host, int64_t m, int32_t seg_l
                             int32_t* item_row, int64_t* item_begin, int32_t* item_len,
                             int32_t* item_slot, int32_t* long_row, int32_t* long_slot0,
                             int32_t* long_nseg);
+/* Chunk table of a filled plan (host arrays in, host arrays out; pure CPU).  hals_als_plan_chunk_count_host returns
+ * the number of chunks, or -1 on invalid input. */
+int64_t hals_als_plan_chunk_count_host(const int32_t* item_len, int64_t n_items);
+int hals_als_plan_chunks_host(const int32_t* item_len, const int64_t* item_begin, const int32_t* item_slot,
+                              int64_t n_items, int64_t* item_chunk0, int64_t* item_cost0, int64_t* chunk_pos,
+                              int32_t* chunk_cnt);
 /* Bytes of device workspace hals_als_half_step needs for a plan with n_slots slots and a
  * source factor matrix of n_src rows (the tensor-core path keeps a bf16 split copy of it). */
 size_t hals_als_workspace_bytes(int64_t n_slots, int k, int64_t n_src);
 /* Default segment length for rank k (ratings per work item). */
 int32_t hals_als_default_seg_len(int k);
+/* out[i] = bf16(vals[i]) | bf16(vals[i] - bf16(vals[i])) << 16 (device arrays); see hals_als_plan.vals_hl. */
+int hals_als_pack_ratings(const float* vals, int64_t nnz, uint32_t* out, void* stream);
 
 int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, const float* vals,
                        int64_t m_dst, const float* src, int64_t n_src, float* dst, int k,

@@ -58,8 +58,36 @@ def test_planner_covers_every_rating_exactly_once():
     assert sorted(lr) == [3, 150] and nl == 2
     assert nslots == sum(ln2) and sorted(slot[slot >= 0]) == list(range(nslots))
     assert set(row) == set(np.nonzero(counts)[0])
-    # long-row slices come first so that the tail of the grid is short rows
-    assert (slot[: nslots] >= 0).all() and (slot[nslots:] < 0).all()
+    # slices are spread evenly among the whole rows: every prefix holds its proportional share (+-1) of the slices
+    sliced = np.cumsum(slot >= 0)
+    want = np.arange(1, ni + 1) * nslots / ni
+    assert np.abs(sliced - want).max() <= 1.0
+    # slot ids keep the order of the ratings inside a row (the slot reduction sums them in slot order)
+    for r in (3, 150):
+        sel = row == r
+        assert list(slot[sel]) == sorted(slot[sel]) and list(beg[sel]) == sorted(beg[sel])
+
+
+def test_chunk_table_matches_the_items():
+    L = nat.lib()
+    rng = np.random.default_rng(1)
+    counts = rng.integers(0, 200, 100)
+    counts[[5, 50]] = [3000, 129]
+    rowptr = np.concatenate([[0], np.cumsum(counts)])
+    (ni, nl, nslots), row, beg, ln, slot, lr, ls, ln2 = _plan(rowptr, 96)
+    nch = L.hals_als_plan_chunk_count_host(nat.ptr(ln), ni)
+    assert nch == int(((ln + 31) // 32).sum())
+    c0, cost0 = np.empty(ni + 1, np.int64), np.empty(ni + 1, np.int64)
+    pos, cnt = np.empty(nch, np.int64), np.empty(nch, np.int32)
+    nat.check(L.hals_als_plan_chunks_host(nat.ptr(ln), nat.ptr(beg), nat.ptr(slot), ni, nat.ptr(c0), nat.ptr(cost0),
+                                          nat.ptr(pos), nat.ptr(cnt)))
+    assert c0[0] == 0 and c0[-1] == nch and (np.diff(c0) == (ln + 31) // 32).all()
+    assert cost0[0] == 0 and (np.diff(cost0) > 0).all()
+    for i in range(ni):
+        ks = np.arange(c0[i], c0[i + 1])
+        assert (pos[ks] == beg[i] + 32 * np.arange(len(ks))).all()
+        assert (cnt[ks] == ln[i] - 32 * np.arange(len(ks))).all() and cnt[ks[-1]] <= 32 < cnt[ks[-1]] + 32
+    assert L.hals_als_plan_chunk_count_host(None, 3) == -1
 
 
 def test_planner_rejects_bad_input():
