@@ -134,6 +134,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* mbar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// Non-blocking variant (try_wait may suspend the thread for a system-dependent time: never alternate two of them in
+// a polling loop -- the barrier that completes first is then noticed only when the other one's suspension ends).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* mbar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // Spins until the phase with the given parity completes.  Bounded: a lost arrival must not hang
 // the GPU box -- after ~4e9 SM cycles (about 2 s) the kernel traps (surfaces as a launch failure).
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
