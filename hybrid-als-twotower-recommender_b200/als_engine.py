@@ -216,8 +216,9 @@ class AlsEngine:
         ratings = torch.as_tensor(ratings).to(self.device, torch.float32).contiguous()
         sse = torch.zeros(1, dtype=torch.float64, device=self.device)
         cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        ws = torch.empty(int(L.hals_als_sse_workspace_bytes()), dtype=torch.uint8, device=self.device)
         nat.check(L.hals_als_sse(nat.ptr(self.X), nat.ptr(self.Y), self.k, nat.ptr(users), nat.ptr(items),
-                                 nat.ptr(ratings), users.numel(), nat.ptr(sse), nat.ptr(cnt),
+                                 nat.ptr(ratings), users.numel(), nat.ptr(sse), nat.ptr(cnt), nat.ptr(ws), ws.numel(),
                                  nat.current_stream()), "hals_als_sse")
         return float(torch.sqrt(sse / cnt.clamp_min(1)).item())
 

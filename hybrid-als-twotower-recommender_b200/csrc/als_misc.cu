@@ -162,12 +162,16 @@ extern "C" int hals_als_predict(const float* X, const float* Y, int k, const int
   return 0;
 }
 
+extern "C" size_t hals_als_sse_workspace_bytes(void) { return 1024 * sizeof(double); }
+
 extern "C" int hals_als_sse(const float* X, const float* Y, int k, const int32_t* users,
                             const int32_t* items, const float* ratings, int64_t n, double* sse,
-                            int64_t* count, void* stream) {
+                            int64_t* count, void* workspace, size_t workspace_bytes, void* stream) {
   HALS_REQUIRE(X && Y && users && items && ratings && sse && count, "null pointer");
-  static thread_local double* part = nullptr;  // 1024 doubles of scratch, allocated once per thread
-  if (!part) HALS_CUDA(cudaMalloc(&part, 1024 * sizeof(double)));
+  HALS_REQUIRE(workspace != nullptr, "null workspace");
+  if (workspace_bytes < hals_als_sse_workspace_bytes()) return fail(HALS_ERR_WORKSPACE, "%s: workspace too small%s", __func__);
+  HALS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "workspace must be 8-byte aligned");
+  double* part = reinterpret_cast<double*>(workspace);   // per-block partial sums (caller-owned: nothing allocates here)
   int nb = (int)((n + 255) / 256);
   if (nb > 1024) nb = 1024;
   if (nb < 1) nb = 1;

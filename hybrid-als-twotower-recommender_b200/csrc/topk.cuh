@@ -105,7 +105,7 @@ __device__ __forceinline__ int topk_compact(uint64_t* buf, int count, int topk, 
 // row buffer by a 32-step bitwise search on the order-preserving score bits (one warp-wide count per
 // step), then keeps every key whose score is >= that threshold, in place.  ~10x cheaper than the
 // bitonic sort; the final ordering is established once, by topk_compact, when the row is finished.
-// Returns the new count (>= keep only through exact score ties) and the threshold score.
+// Returns the new count (min(count, keep): ties at the threshold are broken by item index) and the threshold score.
 template <int CAP>
 __device__ __forceinline__ int topk_select_compact(uint64_t* buf, int count, int keep, int lane, float* thr_out) {
   constexpr int R = CAP / 32;
@@ -127,9 +127,31 @@ __device__ __forceinline__ int topk_select_compact(uint64_t* buf, int count, int
     c = __reduce_add_sync(0xffffffffu, c);
     if (c >= keep) T = cand;
   }
+  // Exactly `keep` survive.  More than `keep` keys at or above T means score ties AT T: of those only the
+  // keep - #(score > T) with the largest low words (= lowest item index, the reference's stable order) stay, found by
+  // the same bitwise search on the low word.  Without this a row of mass ties stays above CAP - W after a compaction
+  // and the next group of columns writes past the end of its buffer.
+  int ge = 0, gt = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) { ge += (hi[r] >= T && hi[r] != 0u) ? 1 : 0; gt += (hi[r] > T) ? 1 : 0; }
+  ge = __reduce_add_sync(0xffffffffu, ge);
+  gt = __reduce_add_sync(0xffffffffu, gt);
+  uint32_t Lmin = 0;
+  if (ge > keep) {
+    const int want = keep - gt;                           // >= 1: T is the keep-th largest score
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = Lmin | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) c += (hi[r] == T && lo[r] >= cand) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= want) Lmin = cand;
+    }
+  }
   int mine = 0;
 #pragma unroll
-  for (int r = 0; r < R; ++r) mine += (hi[r] >= T && hi[r] != 0u) ? 1 : 0;
+  for (int r = 0; r < R; ++r) mine += (hi[r] != 0u && (hi[r] > T || (hi[r] == T && lo[r] >= Lmin))) ? 1 : 0;
   int off = mine;                                        // inclusive warp scan
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -141,7 +163,7 @@ __device__ __forceinline__ int topk_select_compact(uint64_t* buf, int count, int
   __syncwarp();                                          // every lane holds its keys in registers: safe to overwrite
 #pragma unroll
   for (int r = 0; r < R; ++r)
-    if (hi[r] >= T && hi[r] != 0u) buf[off++] = ((uint64_t)hi[r] << 32) | lo[r];
+    if (hi[r] != 0u && (hi[r] > T || (hi[r] == T && lo[r] >= Lmin))) buf[off++] = ((uint64_t)hi[r] << 32) | lo[r];
   __syncwarp();
   *thr_out = f32_from_orderable(T);
   return total;

@@ -12,6 +12,9 @@ namespace hals {
 constexpr int kTowerThreads = 256;
 constexpr int kTowerMaxE = 64;
 
+// rows == 0: table size unknown, no check (ids are then trusted, as in ABI version 1 before the field existed)
+__device__ __forceinline__ bool in_table(int id, int rows) { return rows <= 0 ? id >= 0 : (id >= 0 && id < rows); }
+
 __device__ __forceinline__ void warp_layer_norm_store(float v0, float v1, int E, int lane, const float* g,
                                                       const float* b, float eps, float* out) {
   const bool h0 = lane < E, h1 = lane + 32 < E;
@@ -30,9 +33,11 @@ tower_user_kernel(hals_tower_weights w, const int32_t* __restrict__ ids, int64_t
   const int E = w.embedding_size;
   const int64_t warps = (int64_t)gridDim.x * (kTowerThreads / 32);
   for (int64_t r = (int64_t)blockIdx.x * (kTowerThreads / 32) + (threadIdx.x >> 5); r < n; r += warps) {
-    const float* e = w.user_emb + (int64_t)ids[r] * E;
-    const float v0 = lane < E ? e[lane] : 0.f;
-    const float v1 = lane + 32 < E ? e[lane + 32] : 0.f;
+    const int id = ids[r];
+    const bool ok = in_table(id, w.num_users);            // out-of-range id: zero embedding, no out-of-bounds read
+    const float* e = w.user_emb + (int64_t)(ok ? id : 0) * E;
+    const float v0 = (ok && lane < E) ? e[lane] : 0.f;
+    const float v1 = (ok && lane + 32 < E) ? e[lane + 32] : 0.f;
     warp_layer_norm_store(v0, v1, E, lane, w.user_ln_g, w.user_ln_b, w.ln_eps, out + r * out_stride);
   }
 }
@@ -52,17 +57,19 @@ tower_item_kernel(hals_tower_weights w, const int32_t* __restrict__ item_ids, co
   float* c = cc + warp * C;
   const int64_t warps = (int64_t)gridDim.x * (kTowerThreads / 32);
   for (int64_t r = (int64_t)blockIdx.x * (kTowerThreads / 32) + warp; r < n; r += warps) {
-    const float* ei = w.item_emb + (int64_t)item_ids[r] * E;
-    const float* em = w.manu_emb + (int64_t)manu_ids[r] * MD;
-    const float* ec = w.cat_emb + (int64_t)cat_ids[r] * CD;
+    const int ii = item_ids[r], mi = manu_ids[r], ci = cat_ids[r];
+    const bool oki = in_table(ii, w.num_items), okm = in_table(mi, w.num_manufacturers), okc = in_table(ci, w.num_categories);
+    const float* ei = w.item_emb + (int64_t)(oki ? ii : 0) * E;
+    const float* em = w.manu_emb + (int64_t)(okm ? mi : 0) * MD;
+    const float* ec = w.cat_emb + (int64_t)(okc ? ci : 0) * CD;
     // MinMaxScaler.transform on (price, average_review_rating): x*scale_ + min_
     const float x0 = fmaf(numeric[r * 2 + 0], w.num_scale[0], w.num_offset[0]);
     const float x1 = fmaf(numeric[r * 2 + 1], w.num_scale[1], w.num_offset[1]);
     for (int f = lane; f < C; f += 32) {
       float v;
-      if (f < E) v = ei[f];
-      else if (f < E + MD) v = em[f - E];
-      else if (f < E + MD + CD) v = ec[f - E - MD];
+      if (f < E) v = oki ? ei[f] : 0.f;
+      else if (f < E + MD) v = okm ? em[f - E] : 0.f;
+      else if (f < E + MD + CD) v = okc ? ec[f - E - MD] : 0.f;
       else {
         const int h = f - E - MD - CD;    // Dense(16, relu) on the two numerics
         v = fmaxf(fmaf(x1, w.num_w[H + h], fmaf(x0, w.num_w[h], w.num_b[h])), 0.f);

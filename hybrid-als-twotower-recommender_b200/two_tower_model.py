@@ -79,6 +79,9 @@ class TowerParams:
             sc, mn = (1.0, 1.0), (0.0, 0.0)
         w.num_scale[0], w.num_scale[1] = float(sc[0]), float(sc[1])
         w.num_offset[0], w.num_offset[1] = float(mn[0]), float(mn[1])
+        # table sizes: ids outside a table get a zero embedding in the kernels instead of an out-of-bounds read
+        w.num_users, w.num_items = int(self.t["user_emb"].shape[0]), int(self.t["item_emb"].shape[0])
+        w.num_manufacturers, w.num_categories = int(self.t["manu_emb"].shape[0]), int(self.t["cat_emb"].shape[0])
         return w
 
 

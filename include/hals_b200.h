@@ -129,9 +129,10 @@ int hals_als_predict(const float* X, const float* Y, int k, const int32_t* users
 
 /* Sum of squared errors over n (user,item,rating) triples -> *sse (double, device) and
  * *count (int64, device; pairs with both sides present).  RMSE harness for parity. */
+size_t hals_als_sse_workspace_bytes(void);
 int hals_als_sse(const float* X, const float* Y, int k, const int32_t* users,
                  const int32_t* items, const float* ratings, int64_t n, double* sse,
-                 int64_t* count, void* stream);
+                 int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Two-tower forward.  Replaces the Keras graph built at src/two_tower_model.py:38-89 as
@@ -162,6 +163,9 @@ typedef struct hals_tower_weights {
   float ln_eps;           /* 1e-3 (Keras default) */
   float num_scale[2];
   float num_offset[2];
+  /* Rows of the four embedding tables.  An id outside [0, rows) contributes a zero embedding vector (what Keras'
+   * GPU Embedding op does; its CPU op raises) instead of reading out of bounds.  0 = unknown: no check. */
+  int32_t num_users, num_items, num_manufacturers, num_categories;
 } hals_tower_weights;
 
 int hals_tower_user(const hals_tower_weights* w, const int32_t* user_ids, int64_t n, float* out,

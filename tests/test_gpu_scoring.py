@@ -77,6 +77,37 @@ def test_tensor_core_path_matches_oracle(U, I, ka, kt, k):
     assert sc.flagged_users(U, k) <= max(2, U // 20), "the candidate margin should make exact re-runs rare"
 
 
+@pytest.mark.parametrize("mode", ["few_distinct_items", "duplicated_rows", "zero_als_items"])
+def test_tensor_core_path_with_mass_score_ties(mode):
+    """Many items with EXACTLY equal scores (duplicate feature rows, items without ALS factors): the streaming
+    candidate filter must trim tie groups by item index and never run past a user's candidate buffer."""
+    _, nat, scoring = _pkg()
+    rng = np.random.default_rng(11)
+    U, I, ka, kt, k = 600, 8192, 64, 50, 100
+    Ua, Ut = rng.normal(0, ka ** -0.5, (U, ka)).astype(np.float32), rng.normal(0, 1, (U, kt)).astype(np.float32)
+    if mode == "few_distinct_items":
+        base_a, base_t = rng.normal(0, 1, (7, ka)).astype(np.float32), rng.normal(0, 1, (7, kt)).astype(np.float32)
+        Ia, It = base_a[np.arange(I) % 7], base_t[np.arange(I) % 7]          # 7 distinct scores, ~1170 ties each
+    elif mode == "duplicated_rows":
+        Ia, It = rng.normal(0, 1, (I, ka)).astype(np.float32), rng.normal(0, 1, (I, kt)).astype(np.float32)
+        Ia[1000:1400], It[1000:1400] = Ia[999], It[999]                       # one item repeated 400 times
+        Ia[5000:5300], It[5000:5300] = Ia[4999], It[4999]
+    else:
+        Ia, It = rng.normal(0, 1, (I, ka)).astype(np.float32), np.zeros((I, kt), np.float32)
+        Ia[::3] = 0.0                                                         # a third of the items score exactly 0
+    Ia, It = np.ascontiguousarray(Ia), np.ascontiguousarray(It)
+    sc = scoring.HybridScorer(dev(Ua), dev(Ia), dev(Ut), dev(It))
+    assert int(nat.lib().hals_score_flag_counter_offset(U, I, ka, kt, k)) >= 0, "expected the tensor-core path"
+    sc.extrema()
+    idx, s = sc.recommend(k, 0.8, 0.2)
+    idx, s = idx.cpu().numpy(), s.cpu().numpy()
+    B, _, _ = dense_blend(Ua, Ia, Ut, It, 0.8, 0.2)
+    check_topk_against_dense(B, idx, s, k, TOL * 5)
+    assert (idx >= 0).all() and (idx < I).all()
+    for u in range(0, U, 37):                          # no item twice in a list (a buffer overrun would corrupt neighbours)
+        assert len(set(idx[u].tolist())) == k
+
+
 def test_tensor_core_path_falls_back_exactly_when_bf16_cannot_separate():
     """Items that differ by less than bf16 resolution: the verification must refuse the tensor-core
     candidates and the exact re-run must still produce the oracle answer (incl. a constant model)."""
@@ -100,6 +131,35 @@ def test_tensor_core_path_falls_back_exactly_when_bf16_cannot_separate():
     assert sc.flagged_users(U * reps, k) > 0, "this input must trigger the exact re-run"
     # score ranges are ~1e-2 here, so fp32 cancellation in (s - min)/(max - min) costs ~1e-5 of the [0,1] range
     check_topk_against_dense(B, idx.cpu().numpy(), s.cpu().numpy(), k, 2e-4)
+
+
+def test_tower_ids_outside_the_tables_are_safe():
+    """An id outside an embedding table must not read out of bounds: it contributes a zero vector (Keras' GPU
+    Embedding behaviour), i.e. the user tower outputs LayerNorm(0) = beta."""
+    pkg, nat, scoring = _pkg()
+    from hybrid_als_twotower_recommender_b200.two_tower_model import TowerParams
+    tp = TowerParams.keras_init(20, 30, 5, 4, 50, "cuda", seed=1)
+    tp.t["user_ln_b"] += 0.25                            # a non-trivial beta to recognise
+    w = tp.struct(None)
+    ids = torch.tensor([0, 19, 20, 10**6, -3], dtype=torch.int32, device="cuda")
+    out = torch.full((5, 50), 7.0, device="cuda")
+    nat.check(nat.lib().hals_tower_user(w, nat.ptr(ids), 5, nat.ptr(out), 50, nat.current_stream()))
+    o = out.cpu().numpy()
+    assert np.isfinite(o).all()
+    beta = tp.t["user_ln_b"].cpu().numpy()
+    for r in (2, 3, 4):
+        assert np.allclose(o[r], beta, atol=1e-6)
+    assert not np.allclose(o[0], beta, atol=1e-3)
+    # item tower: every table checked separately
+    n = 4
+    iid = torch.tensor([0, 30, 1, 2], dtype=torch.int32, device="cuda")
+    mid = torch.tensor([0, 0, 5, 1], dtype=torch.int32, device="cuda")
+    cid = torch.tensor([0, 0, 0, -1], dtype=torch.int32, device="cuda")
+    num = torch.rand((n, 2), device="cuda")
+    io = torch.empty((n, 50), device="cuda")
+    nat.check(nat.lib().hals_tower_item(w, nat.ptr(iid), nat.ptr(mid), nat.ptr(cid), nat.ptr(num), n, nat.ptr(io), 50,
+                                        nat.current_stream()))
+    assert torch.isfinite(io).all()
 
 
 def test_reference_fixtures_through_fused_kernels():
