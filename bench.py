@@ -39,31 +39,87 @@ METRIC = "als_ratings_per_sec_per_sweep"
 UNIT = "ratings/s"
 
 
-def synth_coo(w, device, seed=1234):
-    """Zipf item popularity (exponent 1), log-normal user activity, duplicates kept (Spark does not
-    merge them).  Generated on `device` with a fixed seed: identical on every rank."""
+_M64 = (1 << 64) - 1
+
+
+def _s64(x):
+    """Python int -> the signed 64-bit value torch.int64 arithmetic wraps to."""
+    x &= _M64
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def _splitmix64(x):
+    """SplitMix64 finaliser on torch.int64 (two's-complement wrap-around; logical shifts emulated with masks)."""
+    z = x + _s64(0x9E3779B97F4A7C15)
+    z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * _s64(0xBF58476D1CE4E5B9)
+    z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * _s64(0x94D049BB133111EB)
+    return z ^ ((z >> 31) & ((1 << 33) - 1))
+
+
+def _uniform01(n, stream, seed, device):
+    """n doubles in [0,1): a counter-based hash of (seed, stream, index) -- integer arithmetic only, so every rank,
+    every run and the CPU reference arm draw bit-identical numbers (torch.multinomial on CUDA did not: round 1's
+    train RMSE moved by 4e-5 between two identical runs)."""
     import torch
-    g = torch.Generator(device=device).manual_seed(seed)
+    idx = torch.arange(n, dtype=torch.int64, device=device)
+    z = _splitmix64(idx + _s64(seed * 0x632BE59BD9B4E019 + stream * 0xD1342543DE82EF95))
+    return ((z >> 11) & ((1 << 53) - 1)).to(torch.float64) * (1.0 / (1 << 53))
+
+
+def synth_coo(w, device, seed=1234):
+    """Zipf item popularity (exponent 1, popularity not sorted by id), log-normal user activity, duplicates kept (Spark
+    does not merge them).  The two CDFs (138k / 27k entries) are built in numpy on the host; the draws are inverse-CDF
+    lookups of hashed uniforms: deterministic across ranks, runs and devices."""
+    import torch
     U, I, nnz = w["users"], w["items"], w["nnz"]
-    item_p = 1.0 / torch.arange(1, I + 1, device=device, dtype=torch.float64)
-    perm = torch.randperm(I, generator=g, device=device)
-    item_w = torch.empty_like(item_p)
-    item_w[perm] = item_p                                  # popularity not sorted by id
-    user_w = torch.exp(torch.randn(U, generator=g, device=device, dtype=torch.float64) * 1.0)
-    chunks_u, chunks_i = [], []
-    left = nnz
-    while left > 0:
-        n = min(left, 1 << 24)
-        chunks_u.append(torch.multinomial(user_w.float(), n, replacement=True, generator=g))
-        chunks_i.append(torch.multinomial(item_w.float(), n, replacement=True, generator=g))
-        left -= n
-    u = torch.cat(chunks_u).to(torch.int32)
-    i = torch.cat(chunks_i).to(torch.int32)
-    if w["half"]:
-        r = torch.randint(1, 11, (nnz,), generator=g, device=device).float() * 0.5
-    else:
-        r = torch.randint(1, 6, (nnz,), generator=g, device=device).float()
+    rng = np.random.default_rng(seed)
+    item_p = 1.0 / np.arange(1, I + 1, dtype=np.float64)
+    item_w = np.empty(I)
+    item_w[rng.permutation(I)] = item_p
+    user_w = np.exp(rng.standard_normal(U))
+
+    def draw(weights, stream):
+        cdf = np.cumsum(weights)
+        cdf /= cdf[-1]
+        cdf_d = torch.from_numpy(cdf).to(device)
+        out = torch.empty(nnz, dtype=torch.int32, device=device)
+        for lo in range(0, nnz, 1 << 24):                    # bounded temporaries
+            n = min(nnz - lo, 1 << 24)
+            x = _uniform01(n, stream, seed + lo, device)
+            out[lo:lo + n] = torch.searchsorted(cdf_d, x, right=True).clamp_(max=len(weights) - 1).to(torch.int32)
+        return out
+
+    u = draw(user_w, 1)
+    i = draw(item_w, 2)
+    r = torch.empty(nnz, dtype=torch.float32, device=device)
+    for lo in range(0, nnz, 1 << 24):
+        n = min(nnz - lo, 1 << 24)
+        x = _uniform01(n, 3, seed + lo, device)
+        r[lo:lo + n] = ((x * 10).floor() + 1).float() * 0.5 if w["half"] else ((x * 5).floor() + 1).float()
     return u, i, r
+
+
+def coo_checksum(u, i, r):
+    """Order-sensitive 63-bit checksum of the rating triples (wrap-around int64 arithmetic)."""
+    import torch
+    n = u.numel()
+    k = torch.arange(n, dtype=torch.int64, device=u.device)
+    h = (u.to(torch.int64) * 1000003 + i.to(torch.int64)) * 31 + (r * 2).to(torch.int64)
+    return int((_splitmix64(h ^ (k * 0x9E3779B1)).sum().item()) & ((1 << 62) - 1))
+
+
+def assert_same_on_all_ranks(values, what, dev, world):
+    """Every rank must hold the same integers (inputs, shard bounds): max == min over ranks, or the run aborts."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
+    hi, lo = t.clone(), t.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    if not torch.equal(hi, lo):
+        raise RuntimeError(f"ranks disagree on {what}: max {hi.tolist()} min {lo.tolist()}")
 
 
 def algorithmic_bytes(w):
@@ -180,6 +236,10 @@ def run_reference(args, w):
     if rank != 0:
         return
     import torch
+    from oracle import c_oracle
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its children: round 1's N>1 reference arm ran on one core
+    c_oracle.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(os.cpu_count() or 1)
     u, i, r = synth_coo(w, "cpu")
     u, i, r = u.numpy(), i.numpy(), r.numpy()
     vals = []
@@ -226,13 +286,16 @@ def scoring_cpu_baseline(Ua, Ia, Ut, It, k, n_users=128):
 
 
 def scoring_leg(args, dev, rank, world, barrier):
-    """Second headline metric: hybrid scored user-item pairs/s (BASELINE config 5 shape, item-sharded:
-    every rank holds 1.25M items -- 10M at 8 GPUs -- and a slice of the 1M users).  Two fused passes
-    (extrema, blend + top-k) + the cross-shard exchange; device-resident operands, CUDA events, max over ranks."""
+    """Second headline metric: hybrid scored user-item pairs/s at the BASELINE config-5 scale: 1,000,000 users against
+    1.25M items per GPU (10M at 8 GPUs, item-sharded), 128-d ALS + 50-d tower, top-100, users in slabs of 65,536.
+    `value`: operands resident in HBM, CUDA events over the whole pass, max over ranks.  `e2e`: pinned host user ids ->
+    H2D -> gather of the users' rows -> two fused passes (+ extrema all-reduce, all-to-all + merge when sharded) ->
+    D2H of this rank's [U/N, 100] indices and scores, wall clock between barriers.  A 64-user fp64 spot check of the
+    local top-k runs on every rank."""
     import torch
     import torch.distributed as dist
-    from hybrid_als_twotower_recommender_b200.scoring import HybridScorer
-    U, I, k, ka, kt = args.score_users, args.score_items_per_gpu, args.score_topk, 128, 50
+    from hybrid_als_twotower_recommender_b200.scoring import HybridScorer, exchange_topk, merge_lists
+    U, I, k, ka, kt, slab = args.score_users, args.score_items_per_gpu, args.score_topk, 128, 50, args.score_slab
     g = torch.Generator(device=dev).manual_seed(99)
     Ua = torch.randn(U, ka, device=dev, generator=g) * ka ** -0.5
     Ut = torch.nn.functional.layer_norm(torch.randn(U, kt, device=dev, generator=g), (kt,))
@@ -240,22 +303,74 @@ def scoring_leg(args, dev, rank, world, barrier):
     Ia = torch.randn(I, ka, device=dev, generator=gi)
     It = torch.nn.functional.layer_norm(torch.randn(I, kt, device=dev, generator=gi), (kt,))
     sc = HybridScorer(Ua, Ia, Ut, It, item_offset=rank * I, dist_rank=rank, world=world)
-    times = []
-    for it in range(3):
-        barrier()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record(); ex = sc.extrema(); e1.record()
-        idx, s = sc.topk_local(ex, k, 0.8, 0.2)
-        from hybrid_als_twotower_recommender_b200.scoring import exchange_topk, merge_lists
-        fi, fs = exchange_topk(idx, s, rank, world, merge_lists)
-        e2.record()
-        barrier()
-        if it > 0:
-            times.append((e0.elapsed_time(e1), e1.elapsed_time(e2)))
-    t = torch.tensor([float(np.mean([a for a, _ in times])), float(np.mean([b for _, b in times]))], device=dev, dtype=torch.float64)
+    slabs = [(a, min(U, a + slab)) for a in range(0, U, slab)]
+
+    def one_pass(timed):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t1 = t2 = 0.0
+        for (a, b) in slabs:
+            ev[0].record(); ex = sc.extrema(a, b); ev[1].record()
+            idx, s = sc.topk_local(ex, k, 0.8, 0.2, a, b)
+            fi, fs = exchange_topk(idx, s, rank, world, merge_lists)
+            ev[2].record()
+            if timed:
+                torch.cuda.synchronize()
+                t1 += ev[0].elapsed_time(ev[1]); t2 += ev[1].elapsed_time(ev[2])
+        return t1, t2
+
+    sc.extrema(*slabs[0]); sc.recommend(k, 0.8, 0.2, *slabs[0])      # warm-up (workspace, tensor maps)
+    barrier()
+    t1, t2 = one_pass(True)
+    barrier()
+    t = torch.tensor([t1, t2], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t1, t2 = (float(x) for x in t.tolist())
+    flagged = 0
+    # ---- spot check: 64 users of the first slab, local top-k against a dense fp64 blend over this rank's items
+    a, b = slabs[0]
+    ex = sc.extrema(a, b)
+    idx, s = sc.topk_local(ex, k, 0.8, 0.2, a, b)
+    flagged = sc.flagged_users(b - a, k)
+    pick = torch.arange(0, b - a, max(1, (b - a) // 64), device=dev)[:64]
+    exd = ex[pick].double()
+    Sa = Ua[a:b][pick].double() @ Ia.double().T
+    St = Ut[a:b][pick].double() @ It.double().T
+
+    def mm(S, lo, hi):
+        rg = hi - lo
+        return (S - lo[:, None]) * torch.where(rg != 0, 1.0 / torch.where(rg != 0, rg, torch.ones_like(rg)), torch.ones_like(rg))[:, None]
+    B = 0.8 * mm(Sa, exd[:, 0], exd[:, 1]) + 0.2 * mm(St, exd[:, 2], exd[:, 3])
+    wv, wi = torch.topk(B, k, dim=1)
+    got_i, got_s = idx[pick].long() - rank * I, s[pick].double()
+    score_err = float((got_s - wv).abs().max())
+    same = float((got_i == wi).double().mean())
+    kth_gap_ok = bool((torch.gather(B, 1, got_i.clamp(0, I - 1)) >= wv[:, -1:] - 1e-5).all())
+    spot = {"users": int(pick.numel()), "max_abs_score_err": score_err, "index_match": same, "all_within_tie_band": kth_gap_ok,
+            "ok": bool(score_err <= 1e-5 and same >= 0.99 and kth_gap_ok)}
+    del Sa, St, B
+    # ---- end to end: host ids -> top-k lists on the host
+    ids_h = torch.randperm(U, generator=torch.Generator().manual_seed(5)).to(torch.int32).pin_memory()
+    per = [((b - a) + world - 1) // world for (a, b) in slabs]
+    out_i = torch.empty((sum(per), k), dtype=torch.int32).pin_memory()
+    out_s = torch.empty((sum(per), k), dtype=torch.float32).pin_memory()
+    sl = HybridScorer(torch.empty((slab, ka), device=dev), Ia, torch.empty((slab, kt), device=dev), It,
+                      item_offset=rank * I, dist_rank=rank, world=world)
+    barrier()
+    t0 = time.perf_counter()
+    o = 0
+    for j, (a, b) in enumerate(slabs):
+        ids = ids_h[a:b].to(dev, non_blocking=True).long()
+        torch.index_select(Ua, 0, ids, out=sl.Ua[: b - a]); torch.index_select(Ut, 0, ids, out=sl.Ut[: b - a])
+        fi, fs = sl.recommend(k, 0.8, 0.2, 0, b - a)
+        out_i[o:o + fi.shape[0]].copy_(fi, non_blocking=True); out_s[o:o + fi.shape[0]].copy_(fs, non_blocking=True)
+        o += fi.shape[0]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te)
     pairs = float(U) * float(I) * world
     flops = pairs * 2 * (ka + kt)
     try:
@@ -266,16 +381,57 @@ def scoring_leg(args, dev, rank, world, barrier):
     if rank == 0 and not args.no_cpu_baseline:
         cpu = scoring_cpu_baseline(Ua, Ia, Ut, It, k)
     return {"metric": "hybrid_scored_pairs_per_sec", "value": pairs / ((t1 + t2) * 1e-3), "unit": "pairs/s",
-            "cpu_baseline": cpu,
-            "config": {"users": U, "items_per_gpu": I, "items_total": I * world, "k_als": ka, "k_tower": kt, "topk": k,
-                       "weights": [0.8, 0.2], "sharding": "item-sharded, users replicated"},
+            "e2e": {"value": pairs / e2e_s, "unit": "pairs/s", "h2d_bytes": int(U * 4), "d2h_bytes": int(sum(per) * k * 8),
+                    "seconds": e2e_s, "what": "pinned host user ids -> H2D -> row gather -> extrema pass -> blend + top-k pass "
+                    "(+ all-reduce / all-to-all + merge) -> D2H of this rank's top-100 lists"},
+            "cpu_baseline": cpu, "spot_check_fp64": spot,
+            "config": {"users": U, "user_slab": slab, "items_per_gpu": I, "items_total": I * world, "k_als": ka, "k_tower": kt,
+                       "topk": k, "weights": [0.8, 0.2], "sharding": "item-sharded, users replicated"},
             "ms_extrema_pass": t1, "ms_blend_topk_pass": t2,
             "tensor": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak,
                        "achieved_pass2": flops / world / (t2 * 1e-3) / 1e12, "frac_pass2": flops / world / (t2 * 1e-3) / 1e12 / peak,
                        "achieved_both_passes": 2 * flops / world / ((t1 + t2) * 1e-3) / 1e12,
                        "note": "algorithmic flops 2*(128+50) per scored pair per pass, per GPU; pass times include operand "
                                "prep, exact re-scoring and (N>1) the extrema all-reduce / top-k all-to-all + merge"},
-            "users_rerun_exactly": sc.flagged_users(U, k)}
+            "users_rerun_exactly_first_slab": flagged}
+
+
+def c3_leg(args, dev, rank, world, barrier):
+    """BASELINE config 3 (Netflix-prize shape, rank 128) at every N the driver runs: sweep time only (device events,
+    max over ranks), same synthetic generator, same sharding as the headline workload."""
+    import torch
+    import torch.distributed as dist
+    from hybrid_als_twotower_recommender_b200.als_engine import AlsEngine
+    w = WORKLOADS["c3"]
+    u, i, r = synth_coo(w, dev)
+    data_sum = coo_checksum(u, i, r)
+    eng = AlsEngine(u, i, r, w["users"], w["items"], w["rank"], w["reg"], device=dev, dist_rank=rank, world=world)
+    assert_same_on_all_ranks([data_sum] + list(eng.user_bounds) + list(eng.item_bounds), "c3 inputs / shard bounds", dev, world)
+    del u, i, r
+    eng.init_user_factors(1)
+    eng.enable_graphs()
+    for _ in range(3):
+        eng.sweep()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.c3_steps):
+        eng.sweep()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / args.c3_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    b_item, b_user = algorithmic_bytes(w)
+    peak, _ = measured_peaks()
+    out = {"metric": METRIC, "value": w["nnz"] / (ms * 1e-3), "unit": UNIT, "ms_per_sweep": ms, "steps": args.c3_steps,
+           "workload": f"c3: {w['desc']}", "n_gpus": world, "inputs_checksum": data_sum,
+           "roofline_frac": (b_item + b_user) / world / (ms * 1e-3) / 1e9 / peak,
+           "algorithmic_bytes_per_sweep": b_item + b_user}
+    del eng
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -293,7 +449,10 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel / collective individually in the timed sweeps")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     ap.add_argument("--no-scoring", action="store_true", help="skip the hybrid top-k scoring leg (extra.hybrid_topk)")
-    ap.add_argument("--score-users", type=int, default=65536)
+    ap.add_argument("--no-c3", action="store_true", help="skip the config-3 sweep timing (extra.als_c3)")
+    ap.add_argument("--c3-steps", type=int, default=3)
+    ap.add_argument("--score-users", type=int, default=1_000_000)
+    ap.add_argument("--score-slab", type=int, default=65536)
     ap.add_argument("--score-items-per-gpu", type=int, default=1_250_000)
     ap.add_argument("--score-topk", type=int, default=100)
     args = ap.parse_args()
@@ -319,7 +478,10 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
 
     u, i, r = synth_coo(w, dev)
+    data_sum = coo_checksum(u, i, r)
     eng = AlsEngine(u, i, r, w["users"], w["items"], w["rank"], w["reg"], device=dev, dist_rank=rank, world=world)
+    # every rank generated the SAME matrix and derived the SAME shard bounds (the all-gathers rely on it)
+    assert_same_on_all_ranks([data_sum] + list(eng.user_bounds) + list(eng.item_bounds), "inputs / shard bounds", dev, world)
     eng.init_user_factors(1)
 
     def barrier():
@@ -378,10 +540,39 @@ def main():
         if s > 0:
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
         del e
-    te = torch.tensor([float(np.mean(e2e_ms)) if e2e_ms else float("nan")], device=dev, dtype=torch.float64)
+    te = torch.tensor([float(np.mean(e2e_ms)) if e2e_ms else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = args.e2e_sweeps * w["nnz"] / (float(te) * 1e-3)
+    e2e_ms_call = float(te) if e2e_ms else None                      # None (JSON null) when the leg was skipped
+    e2e_value = args.e2e_sweeps * w["nnz"] / (e2e_ms_call * 1e-3) if e2e_ms_call else None
+
+    # ---- the same through the drop-in class: ALSModel.train(DataFrame) with raw 64-bit ids (device-side id
+    # compaction + CSR build + sweeps) and the factors read back; single process only (the class drives one GPU)
+    e2e_api = None
+    if world == 1 and not args.no_e2e:
+        import pandas as pd
+        from hybrid_als_twotower_recommender_b200 import ALSModel
+        df = pd.DataFrame({"userId": hu.numpy().astype(np.int64) * 7 + 3, "itemId": hi.numpy().astype(np.int64) * 5 + 1,
+                           "average_review_rating": hr.numpy().astype(np.float64)})
+        m = ALSModel(rank=w["rank"], max_iter=args.e2e_sweeps, reg_param=w["reg"])
+        m.train(df.iloc[:200_000])                                   # warm-up (lazy initialisation, allocator)
+        api_ms = []
+        for _ in range(args.e2e_steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ok = m.train(df)
+            hXa, hYa = m.model.user_factors.cpu(), m.model.item_factors.cpu()
+            api_ms.append((time.perf_counter() - t0) * 1e3)
+            assert ok and hXa.shape[0] > 0 and torch.isfinite(hYa).all()
+        e2e_api = {"value": args.e2e_sweeps * w["nnz"] / (float(np.mean(api_ms)) * 1e-3), "unit": UNIT,
+                   "ms_per_call": float(np.mean(api_ms)), "sweeps_per_call": args.e2e_sweeps,
+                   "h2d_bytes_per_step": int(w["nnz"] * 20), "d2h_bytes_per_step": int((w["users"] + w["items"]) * w["rank"] * 4),
+                   "what": "ALSModel(rank, max_iter).train(pandas DataFrame with raw int64 ids, float64 ratings) -> factors on the host"}
+        del m, df
+
+    c3_extra = None
+    if not args.no_c3:
+        c3_extra = c3_leg(args, dev, rank, world, barrier)
 
     scoring_extra = None
     if not args.no_scoring:
@@ -393,12 +584,17 @@ def main():
         return
     peak, peak_src = measured_peaks()
     b_item, b_user = algorithmic_bytes(w)
-    traffic = None          # measured DRAM bytes per sweep (both launches), from the committed ncu capture of this workload
+    # DRAM bytes per sweep (both half-step launches) cannot be measured outside a profiler: they come from the committed
+    # `ncu --set full` capture of this workload, stamped with the commit the capture was taken at (stale once the
+    # kernel changes: the note below carries the stamp)
+    traffic, traffic_src = None, "no capture for this workload"
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
-            tr = json.load(f).get(args.workload)
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            trj = json.load(f)
+        tr = trj.get(args.workload)
         if tr and world == 1:
             traffic = sum(tr[h][k] for h in ("item_half", "user_half") for k in ("dram_read_bytes", "dram_write_bytes"))
+            traffic_src = f"profiles/r02_traffic.json, captured at commit {trj.get('captured_at_commit', '?')} ({trj.get('kernel', '?')})"
     except (OSError, ValueError, KeyError):
         traffic = None
     # per-rank share of the algorithmic bytes (rows are nnz-balanced across ranks)
@@ -413,18 +609,26 @@ def main():
                    "train_rmse_after_run": rmse_train},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(w["nnz"] * 12),
                 "d2h_bytes_per_step": int((w["users"] + w["items"]) * w["rank"] * 4), "sweeps_per_call": args.e2e_sweeps,
-                "ms_per_call": float(te), "what": "pinned host COO -> H2D -> CSR build + plan -> sweeps -> factors D2H"},
+                "ms_per_call": e2e_ms_call, "what": "pinned host COO -> H2D -> CSR build + plan -> sweeps -> factors D2H"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                     "traffic_note": "DRAM bytes per sweep (item + user launch) from profiles/r01_traffic.json (ncu --set full); "
-                                     "far below the algorithmic bytes because the gathered factor rows are served by the 126 MB L2",
+                     "traffic_note": f"DRAM bytes per sweep (item + user launch), ncu --set full: {traffic_src}; far below the "
+                                     "algorithmic bytes because the gathered factor rows are served by the 126 MB L2",
                      "kernel": "als half-step (build normal equations + Cholesky solve), item + user launches",
                      "algorithmic_bytes_per_sweep": b_item + b_user, "ms_item_half": t_item, "ms_user_half": t_user,
                      "peak_source": peak_src},
     }
+    extra = {}
+    if e2e_api is not None:
+        line["e2e_api"] = e2e_api
     if scoring_extra is not None:
-        line["extra"] = {"hybrid_topk": scoring_extra}
+        extra["hybrid_topk"] = scoring_extra
+    if c3_extra is not None:
+        extra["als_c3"] = c3_extra
+    if extra:
+        line["extra"] = extra
+    line["config"]["inputs_checksum"] = data_sum
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_run(w, hu.numpy(), hi.numpy(), hr.numpy(), target_nnz=args.cpu_sample)
     print(json.dumps(line))

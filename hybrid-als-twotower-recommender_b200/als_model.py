@@ -80,10 +80,24 @@ class ALSModel:
         self.model = None
         self.spark = None
         self.global_mean = 3.0
-        self.item_features = None
+        self._item_features = None
+        self._train_frame = None
+        self._fallback_table = None
         self.implicit_prefs = implicit_prefs
         self.alpha = alpha
         self.seed = seed
+
+    @property
+    def item_features(self):
+        """itemId -> {'features', 'rating'} (als_model.py:48), built on first use from the training frame."""
+        if self._item_features is None and self._train_frame is not None:
+            self._item_features = get_item_features(self._train_frame)
+        return self._item_features
+
+    @item_features.setter
+    def item_features(self, value):
+        self._item_features = value
+        self._fallback_table = None
 
     def initialize_spark(self):
         try:
@@ -101,14 +115,20 @@ class ALSModel:
             import torch
             from .als_engine import AlsEngine
 
-            self.item_features = get_item_features(data)
-            self.global_mean = data["average_review_rating"].mean()
-
-            user_ids, u = np.unique(data["userId"].values, return_inverse=True)
-            item_ids, i = np.unique(data["itemId"].values, return_inverse=True)
-            r = data["average_review_rating"].values.astype(np.float32)
-            eng = AlsEngine(torch.from_numpy(u.astype(np.int64)), torch.from_numpy(i.astype(np.int64)),
-                            torch.from_numpy(r), len(user_ids), len(item_ids), self.rank, self.reg_param,
+            # The raw columns go to the device as they are; id compaction (what Spark's makeBlocks does with the raw
+            # ids, behind als_model.py:62) and the CSR build both run there.  The item-feature table the cold-id
+            # fallback needs (als_model.py:48) is derived lazily, on first use.
+            self._train_frame = data
+            self._item_features = None
+            dev = torch.device("cuda")
+            uid = torch.from_numpy(np.ascontiguousarray(data["userId"].values)).to(dev)
+            iid = torch.from_numpy(np.ascontiguousarray(data["itemId"].values)).to(dev)
+            r = torch.from_numpy(np.ascontiguousarray(data["average_review_rating"].values, dtype=np.float32)).to(dev)
+            self.global_mean = float(r.double().mean().item())
+            user_ids_d, u = torch.unique(uid, sorted=True, return_inverse=True)
+            item_ids_d, i = torch.unique(iid, sorted=True, return_inverse=True)
+            user_ids, item_ids = user_ids_d.cpu().numpy(), item_ids_d.cpu().numpy()
+            eng = AlsEngine(u, i, r, len(user_ids), len(item_ids), self.rank, self.reg_param,
                             implicit=self.implicit_prefs, alpha=self.alpha)
             if init_user_factors is not None:
                 eng.set_user_factors(init_user_factors)
@@ -140,15 +160,12 @@ class ALSModel:
                     nat.ptr(m.user_factors[urow]), nat.ptr(m.item_factors), m.item_factors.stride(0), m.rank,
                     nat.ptr(ids), ids.numel(), nat.ptr(out), nat.current_stream()), "hals_score_one_user")
                 scores[known] = out.cpu().numpy()
-            final_preds = []
-            for item, s in zip(items, scores):
-                if not np.isnan(s):
-                    final_preds.append((item, float(s)))
-                else:  # cold user / cold item: content-similar fallback, as als_model.py:82-86
-                    similar_items = self._find_similar_items(item)
-                    placeholder = np.mean([self.item_features[sim_item]["rating"]
-                                           for sim_item in similar_items]) if similar_items else self.global_mean
-                    final_preds.append((item, placeholder))
+            # cold user / cold item: content-similar fallback (als_model.py:82-86), all cold items in one launch
+            cold = np.flatnonzero(np.isnan(scores))
+            placeholders = self._fallback_scores([items[j] for j in cold]) if len(cold) else []
+            final_preds = [(item, float(s)) for item, s in zip(items, scores)]
+            for j, ph in zip(cold, placeholders):
+                final_preds[j] = (items[j], ph)
             return final_preds
         except Exception as e:
             print(f"Prediction error: {str(e)}")
@@ -172,6 +189,31 @@ class ALSModel:
         out = out.view(len(urows), len(irows))
         bad = torch.from_numpy((urows < 0)[:, None] | (irows < 0)[None, :]).to(dev)
         return out.masked_fill(bad, float("nan"))
+
+    def _fallback_scores(self, items):
+        """Placeholder rating of every item in `items` (als_model.py:83-86): mean rating of its <= 3 cosine neighbours
+        with similarity > 0.5, else the global mean -- hals_similar_items, one warp per item."""
+        import torch
+        from . import _native as nat
+        feats = self.item_features or {}
+        if self._fallback_table is None:
+            ids = list(feats.keys())
+            F = np.asarray([feats[i]["features"] for i in ids], dtype=np.float64).reshape(len(ids), -1)
+            R = np.asarray([feats[i]["rating"] for i in ids], dtype=np.float64)
+            dev = torch.device("cuda")
+            self._fallback_table = ({item: n for n, item in enumerate(ids)}, torch.from_numpy(np.ascontiguousarray(F)).to(dev),
+                                    torch.from_numpy(R).to(dev))
+        pos, F, R = self._fallback_table
+        if F.shape[0] == 0 or F.shape[1] > 8:
+            return [self.global_mean] * len(items) if F.shape[0] == 0 else [
+                (np.mean([feats[s]["rating"] for s in self._find_similar_items(it)]) if self._find_similar_items(it)
+                 else self.global_mean) for it in items]
+        q = torch.tensor([pos.get(it, -1) for it in items], dtype=torch.int32, device=F.device)
+        out = torch.empty(len(items), dtype=torch.float64, device=F.device)
+        nat.check(nat.lib().hals_similar_items(nat.ptr(F), int(F.shape[1]), nat.ptr(R), int(F.shape[0]), nat.ptr(q), len(items),
+                                               float(self.global_mean), nat.ptr(out), None, nat.current_stream()),
+                  "hals_similar_items")
+        return out.cpu().numpy().tolist()
 
     def _find_similar_items(self, item_id, k=3):
         """Top-k cosine-similar items with similarity > 0.5 (als_model.py:93-104), vectorised."""

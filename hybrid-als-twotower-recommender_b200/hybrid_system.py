@@ -155,14 +155,59 @@ class HybridRecommendationSystem:
         w_als, w_tt = self.fusion_weights()
         item_ids = np.asarray(item_features["itemId"].values)
         out_i, out_s = [], []
+        sc = HybridScorer(Ua, Ia, Ut, It)       # one scorer (items, workspace) for every slab of users
         for u0 in range(0, len(urows), user_chunk):
             u1 = min(len(urows), u0 + user_chunk)
-            sc = HybridScorer(Ua[u0:u1], Ia, Ut[u0:u1], It)
-            idx, s = sc.recommend(top_k, w_als, w_tt)
+            idx, s = sc.recommend(top_k, w_als, w_tt, u0, u1)
             out_i.append(idx.cpu().numpy())
             out_s.append(s.cpu().numpy())
         idx = np.concatenate(out_i)
         return np.where(idx >= 0, item_ids[np.maximum(idx, 0)], -1), np.concatenate(out_s)
+
+    def evaluate_models_batch(self, user_ids, actual_ratings_by_user, item_features, k=10, user_chunk=65536):
+        """evaluate_individual_models (hybrid_system.py:42-55) for many users at once: each model's top-k by its own
+        score (the fused scoring kernels with weights (1,0) / (0,1): min-max scaling does not change a model's order)
+        and F1@k against the users' rated items (hals_f1_at_k).  actual_ratings_by_user: per user a dict / iterable of
+        rated item ids (the keys of the reference's `actual_ratings`).  Returns (als_f1, tt_f1) float32 numpy [U];
+        the sticky scalars als_f1_score / twotower_f1_score are set to the LAST user's values, which is what a loop
+        over evaluate_individual_models leaves behind."""
+        import torch
+        from .evaluation import f1_at_k_batch
+        from .scoring import HybridScorer
+        if not self.models_loaded:
+            raise ValueError("Models not loaded. Call load_models() first.")
+        m = self.als_model.model
+        urows = np.array([m.user_row(u) for u in user_ids], dtype=np.int64)
+        cand_ids = np.asarray(item_features["itemId"].values)
+        irows = m.item_rows(cand_ids)
+        if (urows < 0).any() or (irows < 0).any():
+            raise ValueError("evaluate_models_batch needs users and items known to the ALS model")
+        dev = m.item_factors.device
+        sc = HybridScorer(m.user_factors[torch.from_numpy(urows).to(dev)], m.item_factors[torch.from_numpy(irows).to(dev)],
+                          self.twotower_model.user_vectors(user_ids), self.twotower_model.item_vectors(item_features))
+        order = np.argsort(cand_ids, kind="stable")
+        sorted_ids = cand_ids[order]
+
+        def cand_rows(items):      # rated item ids -> positions in the candidate list (unknown ids cannot be predicted:
+            items = np.asarray(list(items))   # they stay in |actual| through a position past the end)
+            pos = np.searchsorted(sorted_ids, items)
+            pos = np.clip(pos, 0, len(sorted_ids) - 1)
+            ok = sorted_ids[pos] == items
+            extra = len(cand_ids) + np.arange(int((~ok).sum()))
+            return np.concatenate([order[pos[ok]], extra]).astype(np.int32)
+
+        actual = [cand_rows(a.keys() if hasattr(a, "keys") else a) for a in actual_ratings_by_user]
+        f_als, f_tt = [], []
+        for u0 in range(0, len(urows), user_chunk):
+            u1 = min(len(urows), u0 + user_chunk)
+            ia, _ = sc.recommend(k, 1.0, 0.0, u0, u1)
+            it, _ = sc.recommend(k, 0.0, 1.0, u0, u1)
+            f_als.append(f1_at_k_batch(ia, actual[u0:u1], k).cpu().numpy())
+            f_tt.append(f1_at_k_batch(it, actual[u0:u1], k).cpu().numpy())
+        f_als, f_tt = np.concatenate(f_als), np.concatenate(f_tt)
+        if len(f_als):
+            self.als_f1_score, self.twotower_f1_score = float(f_als[-1]), float(f_tt[-1])
+        return f_als, f_tt
 
     def cleanup(self):
         if self.als_model:

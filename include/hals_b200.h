@@ -135,6 +135,26 @@ int hals_als_sse(const float* X, const float* Y, int k, const int32_t* users,
                  int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Batched evaluation around the hot path.
+ *
+ * hals_f1_at_k: F1@k of score-sorted per-user lists against the users' rated items -- compute_f1_score
+ * (src/als_model.py:171-177), the weight selector of src/hybrid_system.py:42-55, for all users at once.
+ *   pred_idx [n_users, pred_stride] item ids (first k entries used; -1 = no entry), actual_items sorted ascending
+ *   within each user's range [actual_rowptr[u], actual_rowptr[u+1]) (duplicates count once, like a Python set).
+ *   f1[u] = 2pr/(p+r), p = tp/k, r = tp/|actual|; 0 when there is nothing to match.  true_positives may be NULL.
+ *
+ * hals_similar_items: the cold-id fallback of src/als_model.py:79-104 for a batch of query items: cosine similarity
+ * (fp64, sklearn's normalise-then-dot) of item `queries[q]` to every other item's feature row, the best three by
+ * (similarity desc, position asc), of which those above 0.5 are kept; out[q] = mean of their ratings, or global_mean
+ * when none qualifies (or the query is out of range).  out_neighbours ([n_queries,3], -1 padded) may be NULL.
+ * ---------------------------------------------------------------------------------- */
+int hals_f1_at_k(const int32_t* pred_idx, int64_t pred_stride, int k, const int64_t* actual_rowptr,
+                 const int32_t* actual_items, int64_t n_users, float* f1, int32_t* true_positives, void* stream);
+int hals_similar_items(const double* features /* [n_items, n_features] */, int n_features /* <= 8 */,
+                       const double* ratings /* [n_items] */, int64_t n_items, const int32_t* queries,
+                       int64_t n_queries, double global_mean, double* out, int32_t* out_neighbours, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Two-tower forward.  Replaces the Keras graph built at src/two_tower_model.py:38-89 as
  * evaluated by Model.predict at src/two_tower_model.py:145.
  *   user:  LN(E_user[id])                                                  (:71-74)

@@ -227,6 +227,16 @@ void oracle_hybrid_topk(const float *Ua, const float *Ia, int ka, const float *U
   }
 }
 
+/* bench.py --impl reference under torch.distributed.run inherits OMP_NUM_THREADS=1: the reference arm asks for every
+ * host core explicitly. */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

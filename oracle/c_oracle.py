@@ -38,6 +38,8 @@ def lib():
         L.oracle_hybrid_topk.restype = None
         L.oracle_hybrid_topk.argtypes = [vp, vp, i32, vp, vp, i32, i64, i64, f64, f64, i32, vp, vp]
         L.oracle_num_threads.restype = i32
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [i32]
         _lib = L
     return _lib
 
@@ -48,6 +50,11 @@ def _p(a):
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n: int):
+    """OpenMP threads of the oracle port (torch.distributed.run exports OMP_NUM_THREADS=1 to its children)."""
+    lib().oracle_set_num_threads(int(n))
 
 
 def als_half_step(rowptr, colidx, vals, src, reg, implicit=False, alpha=1.0,

@@ -74,3 +74,25 @@ def hybrid_topk_dense(Ua, Ia, Ut, It, w_als, w_tt, k):
     B = w_als * mm(Sa) + w_tt * mm(St)
     idx = np.argsort(-B, axis=1, kind="stable")[:, :k]
     return idx.astype(np.int32), np.take_along_axis(B, idx, axis=1)
+
+
+def find_similar_items(item_features, item_id, k=3):
+    """als_model.py:93-104, literally: sklearn cosine_similarity per pair, stable descending sort over the dict order,
+    first k, then the > 0.5 filter."""
+    from sklearn.metrics.pairwise import cosine_similarity
+    try:
+        target = item_features[item_id]
+    except KeyError:
+        return []
+    sims = []
+    for other_id, feats in item_features.items():
+        if other_id == item_id:
+            continue
+        sims.append((other_id, cosine_similarity([target["features"]], [feats["features"]])[0][0]))
+    return [item for item, sim in sorted(sims, key=lambda x: x[1], reverse=True)[:k] if sim > 0.5]
+
+
+def fallback_rating(item_features, item_id, global_mean):
+    """als_model.py:83-85: mean rating of the similar items, else the global mean."""
+    similar = find_similar_items(item_features, item_id)
+    return float(np.mean([item_features[s]["rating"] for s in similar])) if similar else global_mean

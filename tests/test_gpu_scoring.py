@@ -305,9 +305,83 @@ def test_end_to_end_api_against_reference_semantics(tmp_path):
     actual = {int(want_idx[0]): 5.0}
     hrs.get_hybrid_recommendations(user, items, actual_ratings=actual, top_k=5)
     assert hrs.fusion_weights() in ((0.8, 0.2), (0.2, 0.8))
+    # batched weight selector == the per-user one (hybrid_system.py:42-55), user by user
+    users_b = [user, int(uid[0]), int(uid[3])]
+    actuals = [{int(x): 5.0 for x in iid[rng.choice(len(iid), 12, replace=False)]} for _ in users_b]
+    fa, ft = hrs.evaluate_models_batch(users_b, actuals, items)
+    for n, (uu, act) in enumerate(zip(users_b, actuals)):
+        a1, t1 = hrs.evaluate_individual_models(uu, act, items)
+        assert fa[n] == pytest.approx(a1, abs=1e-6) and ft[n] == pytest.approx(t1, abs=1e-6)
     # cold item -> fallback value, cold user -> every item falls back (als_model.py:82-86)
     preds = als.predict_for_user(user, [int(iid[0]), 10_000])
     assert preds[1][0] == 10_000 and preds[1][1] == pytest.approx(als.global_mean)
     cold = als.predict_for_user(99_999, [int(iid[0])])
     assert len(cold) == 1 and np.isfinite(cold[0][1])
     hrs.cleanup()
+
+
+def test_batched_f1_matches_the_reference_function():
+    """hals_f1_at_k against compute_f1_score (src/als_model.py:171-177) user by user: integer arithmetic, exact."""
+    _pkg()
+    from hybrid_als_twotower_recommender_b200.evaluation import f1_at_k_batch
+    rng = np.random.default_rng(8)
+    U, I, k = 300, 500, 10
+    scores = rng.normal(size=(U, I))
+    order = np.argsort(-scores, axis=1, kind="stable")[:, :25].astype(np.int32)
+    order[5, 7:] = -1                                                      # a list shorter than k
+    actual = [rng.choice(I, rng.integers(0, 40), replace=True) for _ in range(U)]   # duplicates and empty sets
+    actual[3] = np.array([], dtype=np.int64)
+    got = f1_at_k_batch(dev(order), actual, k).cpu().numpy()
+    for u in range(U):
+        pred = {int(i): float(scores[u, i]) for i in order[u] if i >= 0} if u == 5 else {int(i): float(scores[u, i]) for i in range(I)}
+        want = hybrid_oracle.compute_f1_score({int(a): 1.0 for a in actual[u]}, pred, k)
+        assert got[u] == pytest.approx(want, abs=1e-7), u
+    assert got[3] == 0.0
+
+
+def test_batched_cold_start_fallback_matches_the_reference_loop():
+    """hals_similar_items against the reference's per-item loop (als_model.py:79-104) restated with sklearn:
+    ties, zero feature rows, items without a neighbour above 0.5, unknown ids."""
+    pkg, nat, _ = _pkg()
+    rng = np.random.default_rng(9)
+    n = 400
+    F = rng.integers(-2, 4, (n, 4)).astype(np.float64)                    # many exact ties and opposite directions
+    F[10] = 0.0
+    F[::7] *= -1.0
+    R = rng.uniform(1, 5, n)
+    feats = {1000 + j * 3: {"features": F[j], "rating": float(R[j])} for j in range(n)}
+    als = pkg.ALSModel()
+    als.item_features = feats
+    als.global_mean = 3.21
+    q = [1000, 1003 + 27, 1000 + 3 * 10, 1000 + 3 * 399, 1000 + 3 * 7, 5, 1000 + 3 * 123]   # incl. unknown ids
+    got = als._fallback_scores(q)
+    for item, g in zip(q, got):
+        assert g == pytest.approx(hybrid_oracle.fallback_rating(feats, item, 3.21), abs=1e-12), item
+    more = [1000 + 3 * j for j in range(0, n, 5)]
+    got = als._fallback_scores(more)
+    want = [hybrid_oracle.fallback_rating(feats, item, 3.21) for item in more]
+    assert np.allclose(got, want, atol=1e-12)
+
+
+def test_train_compacts_raw_ids_on_the_device(tmp_path):
+    """ALSModel.train with sparse, unsorted raw ids: the id compaction runs on the GPU (no host np.unique); the
+    factor tables must be keyed by the sorted raw ids exactly as before."""
+    import pandas as pd
+    from oracle import als_oracle, c_oracle
+    pkg, _, _ = _pkg()
+    rng = np.random.default_rng(31)
+    U, I, nnz = 300, 200, 6000
+    raw_u = rng.choice(10**9, U, replace=False); raw_i = rng.choice(10**6, I, replace=False)
+    u, i = rng.integers(0, U, nnz), rng.integers(0, I, nnz)
+    r = rng.integers(1, 6, nnz).astype(np.float32)
+    df = pd.DataFrame({"userId": raw_u[u], "itemId": raw_i[i], "average_review_rating": r.astype(float)})
+    als = pkg.ALSModel(rank=64, max_iter=3, reg_param=0.1)
+    uid, uinv = np.unique(raw_u[u], return_inverse=True); iid, iinv = np.unique(raw_i[i], return_inverse=True)
+    X0 = als_oracle.init_factors(len(uid), 64, 4)
+    assert als.train(df, init_user_factors=X0) is True
+    assert np.array_equal(als.model.user_ids, uid) and np.array_equal(als.model.item_ids, iid)
+    Xo, Yo = als_oracle.als_fit(uinv, iinv, r, len(uid), len(iid), 64, 3, 0.1, X0, half_step=c_oracle.als_half_step)
+    assert np.abs(als.model.user_factors.cpu().numpy() - Xo).max() <= 1e-3
+    assert np.abs(als.model.item_factors.cpu().numpy() - Yo).max() <= 1e-3
+    assert als.global_mean == pytest.approx(float(r.mean()), abs=1e-6)
+    assert set(als.item_features.keys()) == set(iid.tolist())             # built lazily from the training frame
