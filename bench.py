@@ -533,7 +533,7 @@ def main():
         t0 = time.perf_counter()
         du, di, dr = hu.to(dev, non_blocking=True), hi.to(dev, non_blocking=True), hr.to(dev, non_blocking=True)
         e = AlsEngine(du, di, dr, w["users"], w["items"], w["rank"], w["reg"], device=dev, dist_rank=rank, world=world)
-        e.X.copy_(X0)
+        e.set_user_factors(X0)
         e.fit(args.e2e_sweeps)
         hX.copy_(e.X, non_blocking=True); hY.copy_(e.Y, non_blocking=True)
         barrier()

@@ -60,6 +60,9 @@ SIGNATURES = {
     "hals_als_pack_ratings": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
     "hals_als_half_step": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, ctypes.c_int, c_f32,
                                           ctypes.c_int, c_f32, c_vp, ctypes.POINTER(AlsPlan), c_vp, c_sz, c_vp]),
+    "hals_als_split_factors": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, c_vp]),
+    "hals_als_half_step_split64": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_f32, ctypes.POINTER(AlsPlan), c_vp,
+                                                  c_sz, c_vp]),
     "hals_gram_workspace_bytes": (c_sz, [ctypes.c_int]),
     "hals_gram": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_sz, c_vp]),
     "hals_als_predict": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),

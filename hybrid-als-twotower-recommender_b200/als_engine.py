@@ -67,6 +67,55 @@ def native_half_step(shard: CsrShard, plan: AlsPlanHandle, src: torch.Tensor, ds
         plan.workspace_bytes, nat.current_stream()), "hals_als_half_step")
 
 
+class SplitFactors:
+    """Rank-64 factors in the form the tensor-core kernel gathers: bf16 [rows + 1, 128] = [hi(64) | lo(64)], stored
+    PADDED BY OWNER RANK -- rank q's rows [bounds[q], bounds[q+1]) live at [q * mx, q * mx + n_q) -- so that the
+    all-gather of the freshly solved rows is one in-place equal-size NCCL all-gather (no pack, no unpack, no
+    re-split of the whole matrix on every rank).  The last row (index world * mx) is all zero: the ragged tail of a
+    32-rating chunk gathers it."""
+
+    def __init__(self, bounds, world: int, device):
+        self.bounds = np.asarray(bounds, dtype=np.int64)
+        self.world = world
+        self.sizes = np.diff(self.bounds)
+        self.mx = int(max(1, self.sizes.max()))
+        self.n_rows = world * self.mx                      # index of the zero row
+        self.hl = torch.zeros((self.n_rows + 1, 128), dtype=torch.bfloat16, device=device)
+        # natural row -> padded row
+        owner = np.searchsorted(self.bounds, np.arange(int(self.bounds[-1])), side="right") - 1
+        self.pad_of_h = (owner * self.mx + np.arange(int(self.bounds[-1])) - self.bounds[owner]).astype(np.int64)
+        self.pad_of = torch.from_numpy(self.pad_of_h).to(device)
+
+    def segment(self, rank: int) -> torch.Tensor:
+        return self.hl[rank * self.mx: (rank + 1) * self.mx]
+
+    def load(self, full_fp32: torch.Tensor):
+        """Split a complete natural-order fp32 factor matrix into the padded layout (once, at initialisation)."""
+        L = nat.lib()
+        tmp = torch.empty((full_fp32.shape[0], 128), dtype=torch.bfloat16, device=full_fp32.device)
+        nat.check(L.hals_als_split_factors(nat.ptr(full_fp32), full_fp32.shape[0], 64, nat.ptr(tmp), nat.current_stream()),
+                  "hals_als_split_factors")
+        self.hl[: self.n_rows].zero_()
+        self.hl.index_copy_(0, self.pad_of, tmp)
+
+    def all_gather(self, rank: int, group=None):
+        dist = _dist()
+        if dist is None or self.world == 1:
+            return
+        dist.all_gather_into_tensor(self.hl[: self.n_rows], self.segment(rank), group=group)   # in place
+
+
+def native_half_step_split(shard: CsrShard, plan: AlsPlanHandle, colidx_pad: torch.Tensor, src: SplitFactors,
+                           dst_full: torch.Tensor, dst: SplitFactors, rank: int, reg: float):
+    """Rank 64, explicit: gathers from `src` (split, padded), writes this rank's rows of dst_full (fp32, natural order)
+    and of `dst` (split, padded)."""
+    L = nat.lib()
+    out = dst_full[shard.row_begin: shard.row_end]
+    nat.check(L.hals_als_half_step_split64(
+        nat.ptr(colidx_pad), shard.n_rows, nat.ptr(src.hl), src.n_rows, nat.ptr(out), nat.ptr(dst.segment(rank)), float(reg),
+        plan.struct, nat.ptr(plan.workspace), plan.workspace_bytes, nat.current_stream()), "hals_als_half_step_split64")
+
+
 def native_gram(src: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor):
     L = nat.lib()
     nat.check(L.hals_gram(nat.ptr(src), src.shape[0], src.shape[1], nat.ptr(out), nat.ptr(workspace),
@@ -108,6 +157,16 @@ class AlsEngine:
         self.Y = torch.zeros((n_items, self.k), dtype=torch.float32, device=self.device)
         self.gram = None
         self.gram_ws = None
+        # rank 64, explicit, native kernels: factors also live in split (bf16 hi|lo), owner-padded form; half-steps
+        # exchange the split rows in place and the fp32 replicas of the OTHER ranks' rows are refreshed lazily
+        self.split = None
+        self._fp32_stale = False
+        if (self.k == 64 and not self.implicit and self.device.type == "cuda" and self._half_step is native_half_step
+                and make_plans):
+            self.split = {"X": SplitFactors(self.user_bounds, world, self.device),
+                          "Y": SplitFactors(self.item_bounds, world, self.device)}
+            self.colidx_pad_R = self.split["Y"].pad_of[self.R.colidx.long()].to(torch.int32) if world > 1 else self.R.colidx
+            self.colidx_pad_Rt = self.split["X"].pad_of[self.Rt.colidx.long()].to(torch.int32) if world > 1 else self.Rt.colidx
         self._gather_cache = {}
         self._graphs = None                # (item, user) CUDA graphs after enable_graphs()
         self._graph_launch_counts = (0, 0)
@@ -121,6 +180,15 @@ class AlsEngine:
     # -- factors ---------------------------------------------------------------------------
     def set_user_factors(self, X0):
         self.X.copy_(torch.as_tensor(X0, dtype=torch.float32).to(self.device))
+        self._after_user_init()
+
+    def _after_user_init(self):
+        if self.split is not None:
+            # users without ratings are absent from a Spark model; the stateless half-step zeroes their rows on every
+            # call, the split-form path never touches them: zero them once
+            self.X[~self.user_present] = 0
+            self.split["X"].load(self.X)
+            self._fp32_stale = False
 
     def init_user_factors(self, seed: int = 0):
         """Spark's `initialize` distribution: N(0,1) rows scaled to unit L2 norm."""
@@ -128,6 +196,7 @@ class AlsEngine:
         f = torch.randn((self.n_users, self.k), generator=g, dtype=torch.float32)
         f = f / f.norm(dim=1, keepdim=True).clamp_min(1e-30)
         self.X.copy_(f.to(self.device))
+        self._after_user_init()
 
     def _gram_of(self, src):
         if not self.implicit:
@@ -140,19 +209,40 @@ class AlsEngine:
 
     # -- one sweep = item half-step, then user half-step (Spark's order) ---------------------
     def _item_half_eager(self):
+        if self.split is not None:
+            native_half_step_split(self.Rt, self.plan_Rt, self.colidx_pad_Rt, self.split["X"], self.Y, self.split["Y"],
+                                   self.rank, self.reg)
+            self.split["Y"].all_gather(self.rank)
+            self._fp32_stale = self.world > 1
+            return
         self._half_step(self.Rt, self.plan_Rt, self.X, self.Y, self.k, self.reg, self.implicit, self.alpha,
                         self._gram_of(self.X))
         all_gather_rows(self.Y, self.item_bounds, self.rank, self.world, cache=self._gather_cache)
 
     def _user_half_eager(self):
+        if self.split is not None:
+            native_half_step_split(self.R, self.plan_R, self.colidx_pad_R, self.split["Y"], self.X, self.split["X"],
+                                   self.rank, self.reg)
+            self.split["X"].all_gather(self.rank)
+            self._fp32_stale = self.world > 1
+            return
         self._half_step(self.R, self.plan_R, self.Y, self.X, self.k, self.reg, self.implicit, self.alpha,
                         self._gram_of(self.Y))
         all_gather_rows(self.X, self.user_bounds, self.rank, self.world, cache=self._gather_cache)
+
+    def sync_factors(self):
+        """Sharded split-form runs exchange only the split rows during the sweeps: bring the fp32 replicas of the other
+        ranks' rows up to date (one all-gather per matrix; called by fit() and rmse())."""
+        if self.split is not None and self.world > 1 and self._fp32_stale:
+            all_gather_rows(self.Y, self.item_bounds, self.rank, self.world, cache=self._gather_cache)
+            all_gather_rows(self.X, self.user_bounds, self.rank, self.world, cache=self._gather_cache)
+        self._fp32_stale = False
 
     def item_half_step(self):
         if self._graphs is not None:
             self._graphs[0].replay()
             self.graph_launches += self._graph_launch_counts[0]
+            self._fp32_stale = self.split is not None and self.world > 1
         else:
             self._item_half_eager()
 
@@ -160,6 +250,7 @@ class AlsEngine:
         if self._graphs is not None:
             self._graphs[1].replay()
             self.graph_launches += self._graph_launch_counts[1]
+            self._fp32_stale = self.split is not None and self.world > 1
         else:
             self._user_half_eager()
 
@@ -173,6 +264,7 @@ class AlsEngine:
         if self.device.type != "cuda" or self._half_step is not native_half_step or self.plan_R is None:
             return False
         keep = (self.X.clone(), self.Y.clone())
+        keep_split = None if self.split is None else (self.split["X"].hl.clone(), self.split["Y"].hl.clone(), self._fp32_stale)
         try:
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
@@ -197,6 +289,10 @@ class AlsEngine:
             torch.cuda.synchronize(self.device)
         self.X.copy_(keep[0])
         self.Y.copy_(keep[1])
+        if keep_split is not None:
+            self.split["X"].hl.copy_(keep_split[0])
+            self.split["Y"].hl.copy_(keep_split[1])
+            self._fp32_stale = keep_split[2]
         return ok
 
     def sweep(self):
@@ -206,11 +302,13 @@ class AlsEngine:
     def fit(self, max_iter: int):
         for _ in range(int(max_iter)):
             self.sweep()
+        self.sync_factors()
         return self.X, self.Y
 
     # -- evaluation helpers -------------------------------------------------------------------
     def rmse(self, users, items, ratings) -> float:
         L = nat.lib()
+        self.sync_factors()
         users = torch.as_tensor(users).to(self.device, torch.int32).contiguous()
         items = torch.as_tensor(items).to(self.device, torch.int32).contiguous()
         ratings = torch.as_tensor(ratings).to(self.device, torch.float32).contiguous()

@@ -582,7 +582,7 @@ __host__ __device__ inline int slot_final_stride(int ns) {
 __global__ void __launch_bounds__(64)
 als_reduce_solve64_kernel(const float* __restrict__ workspace, float* __restrict__ dst, float reg,
                           const int32_t* __restrict__ long_row, const int32_t* __restrict__ long_slot0,
-                          const int32_t* __restrict__ long_nseg) {
+                          const int32_t* __restrict__ long_nseg, __nv_bfloat16* __restrict__ dst_hl) {
   constexpr int K = kTcK, LDP = kTcLDP;
   __shared__ __align__(16) float P[3 * kTcLDP];
   const int m = threadIdx.x;
@@ -611,6 +611,11 @@ als_reduce_solve64_kernel(const float* __restrict__ workspace, float* __restrict
     ap[i] = pack2(a[2 * i] + (2 * i == m ? lam : 0.f), a[2 * i + 1] + (2 * i + 1 == m ? lam : 0.f));
   const float x = ldlt64_rows<LDP>(ap, a[64], umma::smem_u32(P), m);
   dst[(int64_t)row * K + m] = x;
+  if (dst_hl) {   // the bf16 hi|lo split the next half-step gathers (same rounding as split_bf16_kernel)
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    dst_hl[(int64_t)row * (2 * K) + m] = h;
+    dst_hl[(int64_t)row * (2 * K) + K + m] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
 }
 
 int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_floats, cudaStream_t st) {
@@ -625,9 +630,10 @@ int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_
   return 0;
 }
 
-int als_launch_reduce_solve64(const float* slots, float* dst, float reg, const hals_als_plan* plan, cudaStream_t st) {
+int als_launch_reduce_solve64(const float* slots, float* dst, float reg, const hals_als_plan* plan, void* dst_hl,
+                              cudaStream_t st) {
   als_reduce_solve64_kernel<<<(unsigned)plan->n_long_rows, 64, 0, st>>>(slots, dst, reg, plan->long_row, plan->long_slot0,
-                                                                        plan->long_nseg);
+                                                                        plan->long_nseg, reinterpret_cast<__nv_bfloat16*>(dst_hl));
   HALS_LAUNCH_CHECK();
   return 0;
 }
@@ -658,7 +664,7 @@ int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* sr
   if (plan->n_long_rows > 0) {
     if (int rc = als_launch_slot_group_sum(slots, plan, kTcK * kTcK + kTcK + 4, st)) return rc;
     als_reduce_solve64_kernel<<<(unsigned)plan->n_long_rows, 64, 0, st>>>(slots, dst, reg, plan->long_row,
-                                                                          plan->long_slot0, plan->long_nseg);
+                                                                          plan->long_slot0, plan->long_nseg, nullptr);
     HALS_LAUNCH_CHECK();
   }
   return 0;

@@ -459,7 +459,7 @@ __device__ __forceinline__ void back_block(const f32x2 (&R)[36], f32x2 (&x2)[8],
 }
 
 __device__ __noinline__ void solver_role(uint32_t slots, uint32_t scratch, Bars* bars, float* __restrict__ dst,
-                                         float* __restrict__ workspace, float reg,
+                                         __nv_bfloat16* __restrict__ dst_hl, float* __restrict__ workspace, float reg,
                                          const int32_t* __restrict__ item_row, const int32_t* __restrict__ item_len,
                                          const int32_t* __restrict__ item_slot, const Range* rg, int w, int lane) {
   const int ti = lane >> 3, tj = lane & 7;
@@ -553,6 +553,13 @@ __device__ __noinline__ void solver_role(uint32_t slots, uint32_t scratch, Bars*
       back_block<1>(R, x2, Y, DI, T, RH, ti, tj, lane, out0, out1);
       back_block<0>(R, x2, Y, DI, T, RH, ti, tj, lane, out0, out1);
       *reinterpret_cast<float2*>(dst + (int64_t)row * K + 2 * lane) = make_float2(out0, out1);
+      if (dst_hl) {   // the bf16 hi|lo split of the row, what the NEXT half-step gathers (no separate split pass)
+        const __nv_bfloat162 h = __floats2bfloat162_rn(out0, out1);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(out0 - __low2float(h), out1 - __high2float(h));
+        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(dst_hl + (int64_t)row * (2 * K));
+        o[lane] = h;
+        o[K / 2 + lane] = l;
+      }
       WS_ACC(t_back);
     }
 #ifdef HALS_WS_PROFILE
@@ -571,7 +578,8 @@ als_ws64_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict__
                 const int32_t* __restrict__ item_row, const int32_t* __restrict__ item_len,
                 const int32_t* __restrict__ item_slot, const int64_t* __restrict__ item_chunk0,
                 const int64_t* __restrict__ item_cost0, const int64_t* __restrict__ chunk_pos,
-                const int32_t* __restrict__ chunk_cnt, int64_t n_items, int zero_row, float* __restrict__ workspace) {
+                const int32_t* __restrict__ chunk_cnt, int64_t n_items, int zero_row, float* __restrict__ workspace,
+                __nv_bfloat16* __restrict__ dst_hl) {
   extern __shared__ uint8_t smem_dyn[];
   __shared__ Bars bars;
   __shared__ Range range;
@@ -624,7 +632,7 @@ als_ws64_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict__
   } else if (warp == kWarpMma) {
     mma_role(sbase, tmem, &bars, &range, chunk_cnt, lane);
   } else {
-    solver_role(slots, scratch + (uint32_t)(warp - kWarpSolver) * kScratchBytes, &bars, dst, workspace, reg, item_row,
+    solver_role(slots, scratch + (uint32_t)(warp - kWarpSolver) * kScratchBytes, &bars, dst, dst_hl, workspace, reg, item_row,
                 item_len, item_slot, &range, warp - kWarpSolver, lane);
   }
 #ifdef HALS_WS_PROFILE
@@ -642,7 +650,8 @@ als_ws64_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict__
 }  // namespace ws64
 
 int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_floats, cudaStream_t st);
-int als_launch_reduce_solve64(const float* slots, float* dst, float reg, const hals_als_plan* plan, cudaStream_t st);
+int als_launch_reduce_solve64(const float* slots, float* dst, float reg, const hals_als_plan* plan, void* dst_hl,
+                              cudaStream_t st);
 
 __global__ void pack_ratings_kernel(const float* __restrict__ vals, int64_t nnz, uint32_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -659,16 +668,23 @@ int als_pack_ratings(const float* vals, int64_t nnz, uint32_t* out, cudaStream_t
   return 0;
 }
 
+// src != nullptr: fp32 source factors, split into `split_buf` first (the stateless C-ABI call).
+// src == nullptr: `split_buf` already holds the split source ([n_src + 1][128] bf16, row n_src all zero) -- the
+// engine keeps the factors in this form across half-steps: every solved row is written as fp32 (dst) AND as its
+// bf16 hi|lo split (dst_hl, same row indexing as dst), so no split pass is needed and a sharded run all-gathers the
+// split rows in place.
 int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const float* src, int64_t n_src, float* dst,
-                       float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st) {
+                       float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl, cudaStream_t st) {
   using namespace ws64;
   __nv_bfloat16* hl = reinterpret_cast<__nv_bfloat16*>(split_buf);
-  const int64_t nthreads = n_src * (K / 8);
-  split_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(src, n_src, K, hl);
-  HALS_LAUNCH_CHECK();
-  // row n_src of the split buffer (inside the workspace's slack): all zero, what the ragged tail of an item gathers
-  HALS_CUDA(cudaMemsetAsync(hl + (size_t)n_src * 2 * K, 0, 4 * K, st));
   HALS_REQUIRE(n_src < (int64_t)1 << 24, "rank-64 kernel: at most 2^24 source rows");
+  if (src != nullptr) {
+    const int64_t nthreads = n_src * (K / 8);
+    split_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(src, n_src, K, hl);
+    HALS_LAUNCH_CHECK();
+    // row n_src of the split buffer (inside the workspace's slack): all zero, what the ragged tail of an item gathers
+    HALS_CUDA(cudaMemsetAsync(hl + (size_t)n_src * 2 * K, 0, 4 * K, st));
+  }
   const size_t smem = (size_t)kStages * kStageBytes + (size_t)kSlots * kSlotBytes + (size_t)kSolvers * kScratchBytes +
                       2 * kGatherScratch + 1024;
   static_assert(kStages * kStageBytes + kSlots * kSlotBytes + kSolvers * kScratchBytes + 2 * kGatherScratch + 1024 <= 227 * 1024 - 1024,
@@ -678,11 +694,12 @@ int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const flo
   if (grid > plan->n_items) grid = plan->n_items;
   als_ws64_kernel<<<(unsigned)grid, kThreads, smem, st>>>(colidx, vals_hl, hl, dst, reg, plan->item_row, plan->item_len,
                                                          plan->item_slot, plan->item_chunk0, plan->item_cost0,
-                                                         plan->chunk_pos, plan->chunk_cnt, plan->n_items, (int)n_src, slots);
+                                                         plan->chunk_pos, plan->chunk_cnt, plan->n_items, (int)n_src, slots,
+                                                         reinterpret_cast<__nv_bfloat16*>(dst_hl));
   HALS_LAUNCH_CHECK();
   if (plan->n_long_rows > 0) {
     if (int rc = als_launch_slot_group_sum(slots, plan, K * K + K + 4, st)) return rc;
-    if (int rc = als_launch_reduce_solve64(slots, dst, reg, plan, st)) return rc;
+    if (int rc = als_launch_reduce_solve64(slots, dst, reg, plan, dst_hl, st)) return rc;
   }
   return 0;
 }

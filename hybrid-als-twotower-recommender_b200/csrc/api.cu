@@ -16,7 +16,8 @@ int als_half_step_tc128(const int32_t* colidx, const float* vals, const float* s
 int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* src, int64_t n_src, float* dst,
                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
 int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const float* src, int64_t n_src, float* dst,
-                       float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
+                       float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl, cudaStream_t st);
+int als_launch_split_bf16(const float* src, int64_t n_src, int k, void* out, cudaStream_t st);
 int als_pack_ratings(const float* vals, int64_t nnz, uint32_t* out, cudaStream_t st);
 }  // namespace hals
 
@@ -142,6 +143,30 @@ extern "C" int hals_als_plan_chunks_host(const int32_t* item_len, const int64_t*
   return 0;
 }
 
+extern "C" int hals_als_split_factors(const float* src, int64_t n_rows, int k, void* out_hl, void* stream) {
+  HALS_REQUIRE(k == 64 || k == 128, "split factors exist for ranks 64 and 128");
+  HALS_REQUIRE(n_rows >= 0, "negative count");
+  if (n_rows == 0) return 0;
+  HALS_REQUIRE(src && out_hl, "null pointer");
+  return als_launch_split_bf16(src, n_rows, k, out_hl, (cudaStream_t)stream);
+}
+
+extern "C" int hals_als_half_step_split64(const int32_t* colidx, int64_t m_dst, const void* src_hl, int64_t n_src,
+                                          float* dst, void* dst_hl, float reg, const hals_als_plan* plan,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+  HALS_REQUIRE(plan != nullptr, "null plan");
+  HALS_REQUIRE(m_dst >= 0 && n_src >= 0, "negative count");
+  if (m_dst == 0 || plan->n_items == 0) return 0;
+  HALS_REQUIRE(colidx && src_hl && dst && dst_hl, "null pointer");
+  HALS_REQUIRE(plan->vals_hl && plan->chunk_pos && plan->chunk_cnt && plan->item_chunk0 && plan->item_cost0,
+               "the plan must carry packed ratings and the chunk table");
+  HALS_REQUIRE(workspace != nullptr, "null workspace");
+  if (workspace_bytes < slot_region_bytes(plan->n_slots, 64) + 16) return fail(HALS_ERR_WORKSPACE, "%s: workspace too small%s", __func__);
+  // rows without ratings are never written: the caller keeps them zero (fp32 and split)
+  return als_half_step_ws64(colidx, plan->vals_hl, nullptr, n_src, dst, reg, plan, (float*)workspace,
+                            const_cast<void*>(src_hl), dst_hl, (cudaStream_t)stream);
+}
+
 extern "C" int hals_als_pack_ratings(const float* vals, int64_t nnz, uint32_t* out, void* stream) {
   HALS_REQUIRE(nnz >= 0, "negative count");
   if (nnz == 0) return 0;
@@ -178,7 +203,7 @@ extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, 
     static const bool old64 = [] { const char* e = getenv("HALS_TC64_IMPL"); return e && e[0] == 'c'; }();
     if (old64 || plan->vals_hl == nullptr || plan->chunk_pos == nullptr)
       return als_half_step_tc64(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
-    return als_half_step_ws64(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split, st);
+    return als_half_step_ws64(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split, nullptr, st);
   }
   return als_half_step_simt(colidx, vals, src, dst, k, reg, implicit, alpha, gram, plan, (float*)workspace, st);
 }

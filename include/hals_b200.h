@@ -114,6 +114,19 @@ int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, const float
                        const hals_als_plan* plan /* device arrays inside */, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Rank 64, factors kept in split form across half-steps (what als_engine does; the stateless call above re-splits
+ * the whole source matrix every time, which is a replicated pass on every rank of a sharded run).
+ *   hals_als_split_factors: out_hl[r] = [bf16(x) (k) | bf16(x - bf16(x)) (k)] for n_rows rows (k = 64 or 128).
+ *   hals_als_half_step_split64: src_hl = split source factors, [n_src + 1] rows of 128 bf16, ROW n_src ALL ZERO (the
+ *     ragged tail of a chunk gathers it); every solved row j is written twice: dst[j] (fp32, 64) and dst_hl[j] (its
+ *     split, 128 bf16) -- dst and dst_hl are indexed by the plan's destination rows.  Rows without ratings are not
+ *     touched.  colidx indexes rows of src_hl (a sharded engine stores the factors padded by owner rank, so that the
+ *     all-gather of the freshly solved rows is in place, and remaps colidx once).  Explicit feedback only. */
+int hals_als_split_factors(const float* src, int64_t n_rows, int k, void* out_hl, void* stream);
+int hals_als_half_step_split64(const int32_t* colidx, int64_t m_dst, const void* src_hl, int64_t n_src, float* dst,
+                               void* dst_hl, float reg, const hals_als_plan* plan, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* Dense Gram Y^T Y ([n,k] -> [k,k], fp32 out).  Replaces Spark's computeYtY (implicit
  * mode) behind src/als_model.py:62.  workspace: hals_gram_workspace_bytes(k). */
 size_t hals_gram_workspace_bytes(int k);
