@@ -54,6 +54,28 @@ def all_gather_rows(full: torch.Tensor, bounds, rank: int, world: int, group=Non
     torch.index_select(recv, 0, st["idx"], out=full)
 
 
+def route_to_owners(users, items, ratings, key, bounds, world: int):
+    """All-to-all of rating triples to the rank that owns row `key` (bounds: [world+1] row ranges).  Triples arrive
+    grouped by source rank, each group in its original order, so contiguous input slices reproduce the single-process
+    rating order inside every row."""
+    dist = _dist()
+    dev = key.device
+    cuts = torch.as_tensor(np.asarray(bounds[1:-1]), device=dev, dtype=key.dtype)
+    owner = torch.bucketize(key, cuts, right=True)
+    order = torch.sort(owner, stable=True).indices
+    send_counts = torch.bincount(owner, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    out = []
+    for t in (users, items, ratings):
+        src = t[order].contiguous()
+        dst = torch.empty(int(sum(rc)), dtype=t.dtype, device=dev)
+        dist.all_to_all_single(dst, src, output_split_sizes=rc, input_split_sizes=sc)
+        out.append(dst)
+    return out
+
+
 def native_half_step(shard: CsrShard, plan: AlsPlanHandle, src: torch.Tensor, dst_full: torch.Tensor,
                      k: int, reg: float, implicit: bool, alpha: float, gram: torch.Tensor | None):
     """dst_full[row_begin:row_end] = solve(shard, src).  The only compute path (CUDA)."""
@@ -127,7 +149,13 @@ class AlsEngine:
 
     def __init__(self, users, items, ratings, n_users: int, n_items: int, rank: int, reg: float,
                  implicit: bool = False, alpha: float = 1.0, device=None, seg_len: int | None = None,
-                 dist_rank: int = 0, world: int = 1, half_step=None, make_plans: bool = True):
+                 dist_rank: int = 0, world: int = 1, half_step=None, make_plans: bool = True,
+                 partitioned: bool = False):
+        """users / items / ratings: the COO triples.  partitioned=False: every rank passes the WHOLE matrix and keeps
+        its row shards.  partitioned=True (world > 1): every rank passes only ITS slice of the triples (rank q the q-th
+        contiguous chunk, so that the concatenation over ranks is the original order); row counts are all-reduced
+        and the triples are routed to the owner of their user row (for R) and of their item row (for R^T) with one
+        all-to-all each -- 1/N of the upload and of the sort per rank."""
         self.k, self.reg, self.implicit, self.alpha = int(rank), float(reg), bool(implicit), float(alpha)
         self.n_users, self.n_items = int(n_users), int(n_items)
         self.rank, self.world = dist_rank, world
@@ -137,9 +165,15 @@ class AlsEngine:
         items = torch.as_tensor(items).to(self.device)
         ratings = torch.as_tensor(ratings).to(self.device, torch.float32)
         self.nnz_total = int(users.numel())
-        # nnz-balanced contiguous row ranges (identical on every rank: computed from global counts)
+        # cost-balanced contiguous row ranges (identical on every rank: computed from global counts)
         ucnt_d = torch.bincount(users.to(torch.int64), minlength=n_users)
         icnt_d = torch.bincount(items.to(torch.int64), minlength=n_items)
+        partitioned = bool(partitioned) and world > 1
+        if partitioned:
+            dist = _dist()
+            dist.all_reduce(ucnt_d)
+            dist.all_reduce(icnt_d)
+            self.nnz_total = int(ucnt_d.sum().item())
         ucnt, icnt = ucnt_d.cpu().numpy(), icnt_d.cpu().numpy()
         self.user_bounds = balanced_row_bounds(ucnt, world)
         self.item_bounds = balanced_row_bounds(icnt, world)
@@ -147,8 +181,15 @@ class AlsEngine:
         self.item_present = torch.from_numpy(icnt > 0).to(self.device)
         ub, ue = int(self.user_bounds[dist_rank]), int(self.user_bounds[dist_rank + 1])
         ib, ie = int(self.item_bounds[dist_rank]), int(self.item_bounds[dist_rank + 1])
-        self.R = build_csr(users, items, ratings, n_users, ub, ue, counts=ucnt_d)    # user rows -> item columns
-        self.Rt = build_csr(items, users, ratings, n_items, ib, ie, counts=icnt_d)   # item rows -> user columns
+        if partitioned:
+            ru, ri, rr = route_to_owners(users, items, ratings, users, self.user_bounds, world)
+            self.R = build_csr(ru, ri, rr, n_users, ub, ue, counts=ucnt_d)
+            ru, ri, rr = route_to_owners(users, items, ratings, items, self.item_bounds, world)
+            self.Rt = build_csr(ri, ru, rr, n_items, ib, ie, counts=icnt_d)
+            del ru, ri, rr
+        else:
+            self.R = build_csr(users, items, ratings, n_users, ub, ue, counts=ucnt_d)    # user rows -> item columns
+            self.Rt = build_csr(items, users, ratings, n_items, ib, ie, counts=icnt_d)   # item rows -> user columns
         self.plan_R = self.plan_Rt = None
         if make_plans:
             self.plan_R = AlsPlanHandle(self.R, self.k, seg_len, n_src=n_items)

@@ -35,11 +35,20 @@ class CsrShard:
         return int(self.colidx.numel())
 
 
-def balanced_row_bounds(counts: np.ndarray, world: int) -> np.ndarray:
-    """Contiguous row ranges with ~equal rating counts (nnz-balanced), one per rank.
+def row_cost(counts: np.ndarray) -> np.ndarray:
+    """Cost of a row in the unit the kernels' work plan uses (csrc/api.cu, hals_als_plan_chunks_host): its 32-rating
+    chunks plus the solve of its normal equations (~6 chunk times).  A half-step costs per rating AND per row: the
+    user side of a MovieLens-shaped matrix is dominated by the solves, so shards balanced on ratings alone leave the
+    rank with the most rows ~15 % behind."""
+    counts = np.asarray(counts, dtype=np.int64)
+    return (counts + 31) // 32 + 6 * (counts > 0)
+
+
+def balanced_row_bounds(counts: np.ndarray, world: int, by_cost: bool = True) -> np.ndarray:
+    """Contiguous row ranges of ~equal cost (see row_cost; by_cost=False: equal rating counts), one per rank.
     Returns int64 [world+1]."""
     n = len(counts)
-    csum = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])
+    csum = np.concatenate([[0], np.cumsum(row_cost(counts) if by_cost else counts, dtype=np.int64)])
     total = csum[-1]
     bounds = np.zeros(world + 1, dtype=np.int64)
     for r in range(1, world):

@@ -40,8 +40,15 @@ def _worker(rank, world, port, case, out_dir):
     from hybrid_als_twotower_recommender_b200 import als_engine, scoring
     z = np.load(case)
     U, I, k = int(z["U"]), int(z["I"]), int(z["k"])
-    eng = als_engine.AlsEngine(z["u"], z["i"], z["r"], U, I, k, 0.1, implicit=bool(z["implicit"]), alpha=4.0,
-                               device="cpu", dist_rank=rank, world=world, half_step=_oracle_half_step, make_plans=False)
+    uu, ii, rr = z["u"], z["i"], z["r"]
+    part = bool(z["partitioned"])
+    if part:      # every rank holds only its contiguous slice of the triples; the engine routes them to the row owners
+        c0, c1 = len(uu) * rank // world, len(uu) * (rank + 1) // world
+        uu, ii, rr = uu[c0:c1], ii[c0:c1], rr[c0:c1]
+    eng = als_engine.AlsEngine(uu, ii, rr, U, I, k, 0.1, implicit=bool(z["implicit"]), alpha=4.0,
+                               device="cpu", dist_rank=rank, world=world, half_step=_oracle_half_step, make_plans=False,
+                               partitioned=part)
+    assert eng.nnz_total == len(z["u"])
     assert eng.R.row_begin == eng.user_bounds[rank] and eng.Rt.row_end == eng.item_bounds[rank + 1]
     eng.set_user_factors(z["X0"])
     X, Y = eng.fit(3)
@@ -66,8 +73,8 @@ def _worker(rank, world, port, case, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("implicit", [False, True])
-def test_two_rank_sharded_fit_and_scoring_equal_single_process(tmp_path, implicit):
+@pytest.mark.parametrize("implicit,partitioned", [(False, False), (True, False), (False, True)])
+def test_two_rank_sharded_fit_and_scoring_equal_single_process(tmp_path, implicit, partitioned):
     rng = np.random.default_rng(5)
     U, I, k, nnz = 91, 57, 6, 1400
     p = 1.0 / np.arange(1, I + 1); p /= p.sum()
@@ -76,7 +83,7 @@ def test_two_rank_sharded_fit_and_scoring_equal_single_process(tmp_path, implici
     X0 = als_oracle.init_factors(U, k, 3)
     Ut, It = rng.normal(size=(U, 5)).astype(np.float32), rng.normal(size=(I, 5)).astype(np.float32)
     case = str(tmp_path / "case.npz")
-    np.savez(case, u=u, i=i, r=r, U=U, I=I, k=k, X0=X0, Ut=Ut, It=It, implicit=implicit)
+    np.savez(case, u=u, i=i, r=r, U=U, I=I, k=k, X0=X0, Ut=Ut, It=It, implicit=implicit, partitioned=partitioned)
     mp.spawn(_worker, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
     Xo, Yo = als_oracle.als_fit(u, i, r, U, I, k, 3, 0.1, X0, implicit=implicit, alpha=4.0,
                                 half_step=c_oracle.als_half_step)
