@@ -28,6 +28,7 @@ class AlsPlan(ctypes.Structure):
         ("seg_len", c_i32), ("max_nseg", c_i32),
         ("item_row", c_vp), ("item_begin", c_vp), ("item_len", c_vp), ("item_slot", c_vp),
         ("long_row", c_vp), ("long_slot0", c_vp), ("long_nseg", c_vp),
+        ("n_long_gt16", c_i64), ("n_long_gt256", c_i64),
         ("n_chunks", c_i64), ("item_chunk0", c_vp), ("item_cost0", c_vp), ("chunk_pos", c_vp), ("chunk_cnt", c_vp),
         ("vals_hl", c_vp),
     ]

@@ -156,6 +156,18 @@ class AlsEngine:
         contiguous chunk, so that the concatenation over ranks is the original order); row counts are all-reduced
         and the triples are routed to the owner of their user row (for R) and of their item row (for R^T) with one
         all-to-all each -- 1/N of the upload and of the sort per rank."""
+        import os
+        import time
+        _t = [time.perf_counter()]
+        _timing = os.environ.get("HALS_ENGINE_TIMING") == "1"
+
+        def _mark(what):
+            if _timing:
+                torch.cuda.synchronize()
+                now = time.perf_counter()
+                if dist_rank == 0:
+                    print(f"[als_engine] {what}: {(now - _t[0]) * 1e3:.2f} ms", flush=True)
+                _t[0] = now
         self.k, self.reg, self.implicit, self.alpha = int(rank), float(reg), bool(implicit), float(alpha)
         self.n_users, self.n_items = int(n_users), int(n_items)
         self.rank, self.world = dist_rank, world
@@ -175,6 +187,7 @@ class AlsEngine:
             dist.all_reduce(icnt_d)
             self.nnz_total = int(ucnt_d.sum().item())
         ucnt, icnt = ucnt_d.cpu().numpy(), icnt_d.cpu().numpy()
+        _mark("upload + row counts")
         self.user_bounds = balanced_row_bounds(ucnt, world)
         self.item_bounds = balanced_row_bounds(icnt, world)
         self.user_present = torch.from_numpy(ucnt > 0).to(self.device)
@@ -190,10 +203,12 @@ class AlsEngine:
         else:
             self.R = build_csr(users, items, ratings, n_users, ub, ue, counts=ucnt_d)    # user rows -> item columns
             self.Rt = build_csr(items, users, ratings, n_items, ib, ie, counts=icnt_d)   # item rows -> user columns
+        _mark("routing + CSR build")
         self.plan_R = self.plan_Rt = None
         if make_plans:
             self.plan_R = AlsPlanHandle(self.R, self.k, seg_len, n_src=n_items)
             self.plan_Rt = AlsPlanHandle(self.Rt, self.k, seg_len, n_src=n_users)
+        _mark("work plans")
         self.X = torch.zeros((n_users, self.k), dtype=torch.float32, device=self.device)
         self.Y = torch.zeros((n_items, self.k), dtype=torch.float32, device=self.device)
         self.gram = None
@@ -208,6 +223,7 @@ class AlsEngine:
                           "Y": SplitFactors(self.item_bounds, world, self.device)}
             self.colidx_pad_R = self.split["Y"].pad_of[self.R.colidx.long()].to(torch.int32) if world > 1 else self.R.colidx
             self.colidx_pad_Rt = self.split["X"].pad_of[self.Rt.colidx.long()].to(torch.int32) if world > 1 else self.Rt.colidx
+        _mark("factor buffers + column remap")
         self._gather_cache = {}
         self._graphs = None                # (item, user) CUDA graphs after enable_graphs()
         self._graph_launch_counts = (0, 0)

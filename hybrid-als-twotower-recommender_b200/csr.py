@@ -129,6 +129,14 @@ class AlsPlanHandle:
         }
         nat.check(L.hals_als_plan_fill_host(nat.ptr(rp), m, self.seg_len, *(nat.ptr(h[n]) for n in (
             "item_row", "item_begin", "item_len", "item_slot", "long_row", "long_slot0", "long_nseg"))), "plan_fill")
+        # long rows by slice count, descending: the slot pre-sum launches only cover the rows that need them
+        n_gt16 = n_gt256 = 0
+        if self.n_long:
+            order = np.argsort(-h["long_nseg"][: self.n_long], kind="stable")
+            for name in ("long_row", "long_slot0", "long_nseg"):
+                h[name][: self.n_long] = h[name][: self.n_long][order]
+            n_gt16 = int((h["long_nseg"][: self.n_long] > 16).sum())
+            n_gt256 = int((h["long_nseg"][: self.n_long] > 256).sum())
         # chunk table (pieces of 32 ratings) + cost prefix: what the persistent rank-64 kernel streams
         self.n_chunks = 0
         if k == 64 and self.n_items > 0:
@@ -153,6 +161,7 @@ class AlsPlanHandle:
             n_items=self.n_items, n_long_rows=self.n_long, n_slots=self.n_slots, seg_len=self.seg_len,
             max_nseg=int(h["long_nseg"][: self.n_long].max()) if self.n_long else 0,
             vals_hl=self.vals_hl.data_ptr() if self.vals_hl is not None else None, n_chunks=self.n_chunks,
+            n_long_gt16=n_gt16 if self.n_long else 0, n_long_gt256=n_gt256 if self.n_long else 0,
             **{n: self.dev[n].data_ptr() for n in h})
         self.workspace_bytes = int(L.hals_als_workspace_bytes(self.n_slots, k, int(n_src)))
         self.workspace = torch.empty(max(self.workspace_bytes, 16), dtype=torch.uint8, device=dev)

@@ -2,6 +2,8 @@
 //   gram      : Spark computeYtY (implicit mode), behind src/als_model.py:62
 //   predict   : ALSModel.transform's fp32 dot, src/als_model.py:75
 //   sse       : RMSE harness for the parity statement (not a reference function)
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hals {
@@ -64,6 +66,8 @@ __global__ void gram_reduce_kernel(const float* __restrict__ partial, int nblock
   for (int b = 0; b < nblocks; ++b) s += (double)partial[(size_t)b * KP * KP + i * KP + j];
   out[e] = (float)s;
 }
+
+int gram_tc(const float* src, int64_t n, int k, float* out, float* partial, cudaStream_t st);   // gram_tc.cu
 
 static int gram_padded(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : 128; }
 static int gram_blocks(int64_t n) {
@@ -138,6 +142,9 @@ extern "C" int hals_gram(const float* src, int64_t n, int k, float* out, void* w
   const int KP = gram_padded(k);
   const int nb = gram_blocks(n);
   float* part = (float*)workspace;
+  // ranks 64 / 128: tcgen05 path (gram_tc.cu); HALS_FORCE_SIMT=1 keeps the CUDA-core kernel (A/B runs, small inputs)
+  static const bool force_simt = [] { const char* e = getenv("HALS_FORCE_SIMT"); return e && e[0] == '1'; }();
+  if ((k == 64 || k == 128) && n >= 2048 && !force_simt) return gram_tc(src, n, k, out, part, st);
   switch (KP) {
     case 16: gram_partial_kernel<16><<<nb, kGramThreads, 0, st>>>(src, n, k, part); break;
     case 32: gram_partial_kernel<32><<<nb, kGramThreads, 0, st>>>(src, n, k, part); break;

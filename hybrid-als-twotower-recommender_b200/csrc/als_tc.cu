@@ -623,7 +623,10 @@ int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_
   for (int stride = 1; stride <= kSlotGroup; stride *= kSlotGroup) {
     if (plan->max_nseg <= stride * kSlotGroup) break;
     const int span = stride * kSlotGroup;
-    dim3 g((unsigned)plan->n_long_rows, (unsigned)((plan->max_nseg + span - 1) / span));
+    // rows sorted by slice count (csr.py): only the first n_long_gt16 / n_long_gt256 need this level
+    const int64_t hint = stride == 1 ? plan->n_long_gt16 : plan->n_long_gt256;
+    const int64_t rows = hint > 0 && hint < plan->n_long_rows ? hint : plan->n_long_rows;
+    dim3 g((unsigned)rows, (unsigned)((plan->max_nseg + span - 1) / span));
     als_slot_group_sum_kernel<<<g, 256, 0, st>>>(slots, plan->long_slot0, plan->long_nseg, slot_floats, stride);
     HALS_LAUNCH_CHECK();
   }

@@ -372,8 +372,12 @@ __device__ __forceinline__ void elim_block(f32x2 (&R)[36], f32x2& bb2, const uin
     const float lj = tj > jm ? l[JR] : 0.f;      // columns <= j are finished
     const f32x2 lj2 = pack2(lj, lj);
     // the diagonal block first: it holds the next pivot, whose reciprocal then overlaps the rest of the column
+    // Rows <= j of the diagonal block are finished, but their multipliers are NOT zeroed: a finished row only owns
+    // entries of finished columns (l = 0 below: untouched) and of the upper triangle inside the diagonal block, which
+    // nothing ever reads (the column publish of a later pivot carries them as row multipliers of finished rows again;
+    // the back substitution reads the strict lower triangle only).  Each half of a packed pair is its own row, so a
+    // runaway value cannot leak into a live one.
     w[JR] = fmul2(w[JR], ninv2);
-    w[JR] = pack2(ti > jm ? lo2(w[JR]) : 0.f, ti + 4 > jm ? hi2(w[JR]) : 0.f);   // rows <= j are finished
     R[tri(JR, JR)] = ffma2(w[JR], lj2, R[tri(JR, JR)]);
     const int jn = jm + 1;
     const float ninv_n = -rcp_fast((jn & 4) ? hi2(R[tri(JR, JR)]) : lo2(R[tri(JR, JR)]));
@@ -388,12 +392,12 @@ __device__ __forceinline__ void elim_block(f32x2 (&R)[36], f32x2& bb2, const uin
       const f32x2 mb = fmul2(wb, ninv2);
       bb2 = ffma2(pack2(act_lo ? lo2(mb) : 0.f, act_hi ? hi2(mb) : 0.f), pack2(zj, zj), bb2);
     }
-    if (jm < 7) {
+    {   // publish column j + 1 (jm == 7: nobody owns "column 8" of the block -- no store, no branch either)
       const uint32_t Pn = P + ((uint32_t)(jn & 1) << 8);
       const bool own = (tj == jn);
 #pragma unroll
       for (int q = JR; q < 8; ++q) sts64_if(own, Pn + oW + q * 8, R[tri(q, JR)]);
-      sts32_if(tj == JR && ti == (jn & 3), Y + (uint32_t)(j + 1) * 4u, (jn & 4) ? hi2(bb2) : lo2(bb2));
+      sts32_if(tj == JR && ti == (jn & 3) && jn < 8, Y + (uint32_t)(j + 1) * 4u, (jn & 4) ? hi2(bb2) : lo2(bb2));
       sts32_if(own && ti == (jn & 3), DI + (uint32_t)(j + 1) * 4u, ninv_n);
       __syncwarp();
     }
@@ -647,6 +651,81 @@ als_ws64_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict__
   if (warp == kWarpDrain) umma::tmem_dealloc(tmem, kAcc * kAccCols);
 }
 
+// Long rows: the slices of a row cut at plan time parked their partial (A, b, n) in workspace slots (rows of more
+// than 16 / 256 slices were pre-summed in groups by als_slot_group_sum_kernel).  One CTA per long row: 128 threads sum
+// the remaining <= 16 partials in slot order (coalesced, deterministic), warp 0 solves with the same one-warp LDL^T as
+// the main kernel.  Replaces the round-1 reduce kernel (thread = matrix row, a CTA barrier per pivot: 20-48 us).
+__global__ void __launch_bounds__(128)
+als_reduce_solve64_warp_kernel(const float* __restrict__ workspace, float* __restrict__ dst,
+                               __nv_bfloat16* __restrict__ dst_hl, float reg, const int32_t* __restrict__ long_row,
+                               const int32_t* __restrict__ long_slot0, const int32_t* __restrict__ long_nseg, int final_stride_1,
+                               int final_stride_2) {
+  constexpr int SF = K * K + K + 4;
+  __shared__ __align__(16) float sA[SF];
+  __shared__ __align__(16) uint8_t sScratch[kScratchBytes];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int row = long_row[blockIdx.x];
+  const int s0 = long_slot0[blockIdx.x], ns = long_nseg[blockIdx.x];
+  const int stride = ns > final_stride_2 ? final_stride_2 : ns > final_stride_1 ? final_stride_1 : 1;
+  for (int e = tid * 4; e < SF; e += 128 * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < ns; q += stride) {
+      const float4 v = *reinterpret_cast<const float4*>(workspace + (size_t)(s0 + q) * SF + e);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(sA + e) = acc;
+  }
+  __syncthreads();
+  if (tid >= 32) return;
+  const int ti = lane >> 3, tj = lane & 7;
+  const float lam = reg * sA[K * K + K];
+  f32x2 R[36];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+#pragma unroll
+    for (int c = 0; c <= q; ++c) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = ti + 4 * h + 8 * q, n = tj + 8 * c;
+        v[h] = sA[m * K + n] + (m == n ? lam : 0.f);
+      }
+      R[tri(q, c)] = pack2(v[0], v[1]);
+    }
+  }
+  f32x2 bb2 = pack2(sA[K * K + ti + 8 * tj], sA[K * K + ti + 4 + 8 * tj]);
+  const uint32_t P = umma::smem_u32(sScratch), Y = P + 512, DI = Y + 256, T = DI + 256, RH = T + 256;
+  elim_block<0>(R, bb2, P, Y, DI, ti, tj, lane);
+  elim_block<1>(R, bb2, P, Y, DI, ti, tj, lane);
+  elim_block<2>(R, bb2, P, Y, DI, ti, tj, lane);
+  elim_block<3>(R, bb2, P, Y, DI, ti, tj, lane);
+  elim_block<4>(R, bb2, P, Y, DI, ti, tj, lane);
+  elim_block<5>(R, bb2, P, Y, DI, ti, tj, lane);
+  elim_block<6>(R, bb2, P, Y, DI, ti, tj, lane);
+  elim_block<7>(R, bb2, P, Y, DI, ti, tj, lane);
+  __syncwarp();
+  f32x2 x2[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) x2[q] = 0ull;
+  float out0 = 0.f, out1 = 0.f;
+  back_block<7>(R, x2, Y, DI, T, RH, ti, tj, lane, out0, out1);
+  back_block<6>(R, x2, Y, DI, T, RH, ti, tj, lane, out0, out1);
+  back_block<5>(R, x2, Y, DI, T, RH, ti, tj, lane, out0, out1);
+  back_block<4>(R, x2, Y, DI, T, RH, ti, tj, lane, out0, out1);
+  back_block<3>(R, x2, Y, DI, T, RH, ti, tj, lane, out0, out1);
+  back_block<2>(R, x2, Y, DI, T, RH, ti, tj, lane, out0, out1);
+  back_block<1>(R, x2, Y, DI, T, RH, ti, tj, lane, out0, out1);
+  back_block<0>(R, x2, Y, DI, T, RH, ti, tj, lane, out0, out1);
+  *reinterpret_cast<float2*>(dst + (int64_t)row * K + 2 * lane) = make_float2(out0, out1);
+  if (dst_hl) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(out0, out1);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(out0 - __low2float(h), out1 - __high2float(h));
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(dst_hl + (int64_t)row * (2 * K));
+    o[lane] = h;
+    o[K / 2 + lane] = l;
+  }
+}
+
 }  // namespace ws64
 
 int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_floats, cudaStream_t st);
@@ -699,7 +778,10 @@ int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const flo
   HALS_LAUNCH_CHECK();
   if (plan->n_long_rows > 0) {
     if (int rc = als_launch_slot_group_sum(slots, plan, K * K + K + 4, st)) return rc;
-    if (int rc = als_launch_reduce_solve64(slots, dst, reg, plan, dst_hl, st)) return rc;
+    // level strides of the slot pre-sums (als_tc.cu: kSlotGroup = 16)
+    als_reduce_solve64_warp_kernel<<<(unsigned)plan->n_long_rows, 128, 0, st>>>(
+        slots, dst, reinterpret_cast<__nv_bfloat16*>(dst_hl), reg, plan->long_row, plan->long_slot0, plan->long_nseg, 16, 256);
+    HALS_LAUNCH_CHECK();
   }
   return 0;
 }

@@ -30,7 +30,9 @@ extern "C" const char* hals_last_error(void) { return g_last_error; }
 extern "C" int64_t hals_launch_count(void) { return g_launch_count.load(); }
 extern "C" int hals_max_rank(void) { return 128; }
 
-extern "C" int32_t hals_als_default_seg_len(int k) { return k <= 32 ? 8192 : 4096; }
+// rank 64: a slice is 256 chunks of the persistent kernel (~6 % of a CTA's share on the MovieLens-20M shape) and the
+// hottest rows stay below 256 slices, i.e. one level of slot pre-sums
+extern "C" int32_t hals_als_default_seg_len(int k) { return k <= 64 ? 8192 : 4096; }
 
 static size_t slot_region_bytes(int64_t n_slots, int k) {
   const size_t KP = (size_t)padded_rank(k);

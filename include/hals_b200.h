@@ -72,6 +72,9 @@ typedef struct hals_als_plan {
   const int32_t* long_row;   /* [n_long_rows] destination row                              */
   const int32_t* long_slot0; /* [n_long_rows] first slot                                   */
   const int32_t* long_nseg;  /* [n_long_rows] number of slots                              */
+  /* Optional: when the long-row arrays are sorted by long_nseg DESCENDING, the number of rows with more than 16 and
+   * more than 256 slices -- the slot pre-sum launches then cover only those rows.  0 = unknown (all long rows). */
+  int64_t n_long_gt16, n_long_gt256;
   /* Chunk table (optional; hals_als_plan_chunks_host).  The ratings of work item i, cut into pieces of 32, are chunks
    * [item_chunk0[i], item_chunk0[i+1]); the persistent rank-64 kernel gives every CTA a CONTIGUOUS range of items of
    * equal cost (item_cost0 = prefix sum of chunks + a per-item solve / park cost) and streams its chunks. */
