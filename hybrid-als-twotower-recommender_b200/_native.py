@@ -55,14 +55,14 @@ SIGNATURES = {
     "hals_als_plan_count_host": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "hals_als_plan_fill_host": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hals_als_plan_chunk_count_host": (c_i64, [c_vp, c_i64]),
-    "hals_als_plan_chunks_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "hals_als_plan_chunks_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
     "hals_als_workspace_bytes": (c_sz, [c_i64, ctypes.c_int, c_i64]),
     "hals_als_default_seg_len": (c_i32, [ctypes.c_int]),
     "hals_als_pack_ratings": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
     "hals_als_half_step": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, ctypes.c_int, c_f32,
                                           ctypes.c_int, c_f32, c_vp, ctypes.POINTER(AlsPlan), c_vp, c_sz, c_vp]),
     "hals_als_split_factors": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, c_vp]),
-    "hals_als_half_step_split64": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_f32, ctypes.POINTER(AlsPlan), c_vp,
+    "hals_als_half_step_split": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, ctypes.c_int, c_f32, ctypes.POINTER(AlsPlan), c_vp,
                                                   c_sz, c_vp]),
     "hals_gram_workspace_bytes": (c_sz, [ctypes.c_int]),
     "hals_gram": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, c_vp, c_sz, c_vp]),

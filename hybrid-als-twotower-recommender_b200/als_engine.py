@@ -90,19 +90,20 @@ def native_half_step(shard: CsrShard, plan: AlsPlanHandle, src: torch.Tensor, ds
 
 
 class SplitFactors:
-    """Rank-64 factors in the form the tensor-core kernel gathers: bf16 [rows + 1, 128] = [hi(64) | lo(64)], stored
+    """Rank-64 / rank-128 factors in the form the tensor-core kernels gather: bf16 [rows + 1, 2k] = [hi(k) | lo(k)], stored
     PADDED BY OWNER RANK -- rank q's rows [bounds[q], bounds[q+1]) live at [q * mx, q * mx + n_q) -- so that the
     all-gather of the freshly solved rows is one in-place equal-size NCCL all-gather (no pack, no unpack, no
     re-split of the whole matrix on every rank).  The last row (index world * mx) is all zero: the ragged tail of a
     32-rating chunk gathers it."""
 
-    def __init__(self, bounds, world: int, device):
+    def __init__(self, bounds, world: int, device, k: int = 64):
         self.bounds = np.asarray(bounds, dtype=np.int64)
         self.world = world
+        self.k = int(k)
         self.sizes = np.diff(self.bounds)
         self.mx = int(max(1, self.sizes.max()))
         self.n_rows = world * self.mx                      # index of the zero row
-        self.hl = torch.zeros((self.n_rows + 1, 128), dtype=torch.bfloat16, device=device)
+        self.hl = torch.zeros((self.n_rows + 1, 2 * self.k), dtype=torch.bfloat16, device=device)
         # natural row -> padded row
         owner = np.searchsorted(self.bounds, np.arange(int(self.bounds[-1])), side="right") - 1
         self.pad_of_h = (owner * self.mx + np.arange(int(self.bounds[-1])) - self.bounds[owner]).astype(np.int64)
@@ -114,8 +115,8 @@ class SplitFactors:
     def load(self, full_fp32: torch.Tensor):
         """Split a complete natural-order fp32 factor matrix into the padded layout (once, at initialisation)."""
         L = nat.lib()
-        tmp = torch.empty((full_fp32.shape[0], 128), dtype=torch.bfloat16, device=full_fp32.device)
-        nat.check(L.hals_als_split_factors(nat.ptr(full_fp32), full_fp32.shape[0], 64, nat.ptr(tmp), nat.current_stream()),
+        tmp = torch.empty((full_fp32.shape[0], 2 * self.k), dtype=torch.bfloat16, device=full_fp32.device)
+        nat.check(L.hals_als_split_factors(nat.ptr(full_fp32), full_fp32.shape[0], self.k, nat.ptr(tmp), nat.current_stream()),
                   "hals_als_split_factors")
         self.hl[: self.n_rows].zero_()
         self.hl.index_copy_(0, self.pad_of, tmp)
@@ -129,13 +130,13 @@ class SplitFactors:
 
 def native_half_step_split(shard: CsrShard, plan: AlsPlanHandle, colidx_pad: torch.Tensor, src: SplitFactors,
                            dst_full: torch.Tensor, dst: SplitFactors, rank: int, reg: float):
-    """Rank 64, explicit: gathers from `src` (split, padded), writes this rank's rows of dst_full (fp32, natural order)
+    """Ranks 64 and 128, explicit: gathers from `src` (split, padded), writes this rank's rows of dst_full (fp32, natural order)
     and of `dst` (split, padded)."""
     L = nat.lib()
     out = dst_full[shard.row_begin: shard.row_end]
-    nat.check(L.hals_als_half_step_split64(
-        nat.ptr(colidx_pad), shard.n_rows, nat.ptr(src.hl), src.n_rows, nat.ptr(out), nat.ptr(dst.segment(rank)), float(reg),
-        plan.struct, nat.ptr(plan.workspace), plan.workspace_bytes, nat.current_stream()), "hals_als_half_step_split64")
+    nat.check(L.hals_als_half_step_split(
+        nat.ptr(colidx_pad), shard.n_rows, nat.ptr(src.hl), src.n_rows, nat.ptr(out), nat.ptr(dst.segment(rank)), src.k,
+        float(reg), plan.struct, nat.ptr(plan.workspace), plan.workspace_bytes, nat.current_stream()), "hals_als_half_step_split")
 
 
 def native_gram(src: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor):
@@ -188,8 +189,8 @@ class AlsEngine:
             self.nnz_total = int(ucnt_d.sum().item())
         ucnt, icnt = ucnt_d.cpu().numpy(), icnt_d.cpu().numpy()
         _mark("upload + row counts")
-        self.user_bounds = balanced_row_bounds(ucnt, world)
-        self.item_bounds = balanced_row_bounds(icnt, world)
+        self.user_bounds = balanced_row_bounds(ucnt, world, k=self.k)
+        self.item_bounds = balanced_row_bounds(icnt, world, k=self.k)
         self.user_present = torch.from_numpy(ucnt > 0).to(self.device)
         self.item_present = torch.from_numpy(icnt > 0).to(self.device)
         ub, ue = int(self.user_bounds[dist_rank]), int(self.user_bounds[dist_rank + 1])
@@ -213,14 +214,14 @@ class AlsEngine:
         self.Y = torch.zeros((n_items, self.k), dtype=torch.float32, device=self.device)
         self.gram = None
         self.gram_ws = None
-        # rank 64, explicit, native kernels: factors also live in split (bf16 hi|lo), owner-padded form; half-steps
+        # ranks 64 and 128, explicit, native kernels: factors also live in split (bf16 hi|lo), owner-padded form; half-steps
         # exchange the split rows in place and the fp32 replicas of the OTHER ranks' rows are refreshed lazily
         self.split = None
         self._fp32_stale = False
-        if (self.k == 64 and not self.implicit and self.device.type == "cuda" and self._half_step is native_half_step
+        if (self.k in (64, 128) and not self.implicit and self.device.type == "cuda" and self._half_step is native_half_step
                 and make_plans):
-            self.split = {"X": SplitFactors(self.user_bounds, world, self.device),
-                          "Y": SplitFactors(self.item_bounds, world, self.device)}
+            self.split = {"X": SplitFactors(self.user_bounds, world, self.device, self.k),
+                          "Y": SplitFactors(self.item_bounds, world, self.device, self.k)}
             self.colidx_pad_R = self.split["Y"].pad_of[self.R.colidx.long()].to(torch.int32) if world > 1 else self.R.colidx
             self.colidx_pad_Rt = self.split["X"].pad_of[self.Rt.colidx.long()].to(torch.int32) if world > 1 else self.Rt.colidx
         _mark("factor buffers + column remap")

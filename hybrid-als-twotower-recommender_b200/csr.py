@@ -35,20 +35,20 @@ class CsrShard:
         return int(self.colidx.numel())
 
 
-def row_cost(counts: np.ndarray) -> np.ndarray:
+def row_cost(counts: np.ndarray, k: int = 64) -> np.ndarray:
     """Cost of a row in the unit the kernels' work plan uses (csrc/api.cu, hals_als_plan_chunks_host): its 32-rating
-    chunks plus the solve of its normal equations (~6 chunk times).  A half-step costs per rating AND per row: the
+    chunks plus the solve of its normal equations (~6 chunk times at rank <= 64, ~32 at rank 128).  A half-step costs per rating AND per row: the
     user side of a MovieLens-shaped matrix is dominated by the solves, so shards balanced on ratings alone leave the
     rank with the most rows ~15 % behind."""
     counts = np.asarray(counts, dtype=np.int64)
-    return (counts + 31) // 32 + 6 * (counts > 0)
+    return (counts + 31) // 32 + (32 if k > 64 else 6) * (counts > 0)
 
 
-def balanced_row_bounds(counts: np.ndarray, world: int, by_cost: bool = True) -> np.ndarray:
+def balanced_row_bounds(counts: np.ndarray, world: int, by_cost: bool = True, k: int = 64) -> np.ndarray:
     """Contiguous row ranges of ~equal cost (see row_cost; by_cost=False: equal rating counts), one per rank.
     Returns int64 [world+1]."""
     n = len(counts)
-    csum = np.concatenate([[0], np.cumsum(row_cost(counts) if by_cost else counts, dtype=np.int64)])
+    csum = np.concatenate([[0], np.cumsum(row_cost(counts, k) if by_cost else counts, dtype=np.int64)])
     total = csum[-1]
     bounds = np.zeros(world + 1, dtype=np.int64)
     for r in range(1, world):
@@ -137,23 +137,23 @@ class AlsPlanHandle:
                 h[name][: self.n_long] = h[name][: self.n_long][order]
             n_gt16 = int((h["long_nseg"][: self.n_long] > 16).sum())
             n_gt256 = int((h["long_nseg"][: self.n_long] > 256).sum())
-        # chunk table (pieces of 32 ratings) + cost prefix: what the persistent rank-64 kernel streams
+        # chunk table (pieces of 32 ratings) + cost prefix: what the persistent rank-64 / rank-128 kernels stream
         self.n_chunks = 0
-        if k == 64 and self.n_items > 0:
+        if k in (64, 128) and self.n_items > 0:
             self.n_chunks = int(L.hals_als_plan_chunk_count_host(nat.ptr(h["item_len"]), self.n_items))
             h["item_chunk0"] = np.empty(self.n_items + 1, np.int64)
             h["item_cost0"] = np.empty(self.n_items + 1, np.int64)
             h["chunk_pos"] = np.empty(max(self.n_chunks, 1), np.int64)
             h["chunk_cnt"] = np.empty(max(self.n_chunks, 1), np.int32)
             nat.check(L.hals_als_plan_chunks_host(nat.ptr(h["item_len"]), nat.ptr(h["item_begin"]), nat.ptr(h["item_slot"]),
-                                                  self.n_items, nat.ptr(h["item_chunk0"]), nat.ptr(h["item_cost0"]),
+                                                  self.n_items, int(k), nat.ptr(h["item_chunk0"]), nat.ptr(h["item_cost0"]),
                                                   nat.ptr(h["chunk_pos"]), nat.ptr(h["chunk_cnt"])), "plan_chunks")
         self.host = h
         dev = device if device is not None else shard.colidx.device
         self.dev = {n: torch.from_numpy(a).to(dev) for n, a in h.items()}
-        # ratings as bf16 hi|lo pairs, packed once: the rank-64 tensor-core kernel copies them into its operand
+        # ratings as bf16 hi|lo pairs, packed once: the tensor-core kernels copy them into its operand
         self.vals_hl = None
-        if k == 64 and torch.device(dev).type == "cuda" and shard.vals.numel() > 0:
+        if k in (64, 128) and torch.device(dev).type == "cuda" and shard.vals.numel() > 0:
             self.vals_hl = torch.empty(shard.vals.numel(), dtype=torch.int32, device=dev)
             nat.check(L.hals_als_pack_ratings(nat.ptr(shard.vals), shard.vals.numel(), nat.ptr(self.vals_hl),
                                               nat.current_stream()), "hals_als_pack_ratings")

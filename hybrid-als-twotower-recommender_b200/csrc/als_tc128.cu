@@ -473,7 +473,7 @@ als_tc128_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ v
 __global__ void __launch_bounds__(128)
 als_reduce_solve128_kernel(const float* __restrict__ workspace, float* __restrict__ dst, float reg,
                            const int32_t* __restrict__ long_row, const int32_t* __restrict__ long_slot0,
-                           const int32_t* __restrict__ long_nseg, int slot_group) {
+                           const int32_t* __restrict__ long_nseg, int slot_group, __nv_bfloat16* __restrict__ dst_hl) {
   constexpr int K = k8K;
   __shared__ __align__(16) float PS[2 * k8LDP + 128];
   const int m = threadIdx.x;
@@ -502,6 +502,11 @@ als_reduce_solve128_kernel(const float* __restrict__ workspace, float* __restric
   const uint32_t P = umma::smem_u32(PS);
   const float x = ldlt128_rows(ap, bm, P, P + 2 * k8LDP * 4, m, 1);
   dst[(int64_t)row * K + m] = x;
+  if (dst_hl) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    dst_hl[(int64_t)row * (2 * K) + m] = h;
+    dst_hl[(int64_t)row * (2 * K) + K + m] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
 }
 
 int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_floats, cudaStream_t st);   // als_tc.cu
@@ -524,9 +529,19 @@ int als_half_step_tc128(const int32_t* colidx, const float* vals, const float* s
     constexpr int kGroup = 16;                            // == kSlotGroup of als_tc.cu
     if (int rc = als_launch_slot_group_sum(slots, plan, (int)k8SlotFloats, st)) return rc;
     als_reduce_solve128_kernel<<<(unsigned)plan->n_long_rows, 128, 0, st>>>(slots, dst, reg, plan->long_row,
-                                                                            plan->long_slot0, plan->long_nseg, kGroup);
+                                                                            plan->long_slot0, plan->long_nseg, kGroup, nullptr);
     HALS_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// the long-row tail of the warp-specialised kernel (als_ws128.cu); the slot groups are already pre-summed
+int als_launch_reduce_solve128(const float* slots, float* dst, float reg, const hals_als_plan* plan, void* dst_hl,
+                               cudaStream_t st) {
+  als_reduce_solve128_kernel<<<(unsigned)plan->n_long_rows, 128, 0, st>>>(slots, dst, reg, plan->long_row, plan->long_slot0,
+                                                                          plan->long_nseg, 16,
+                                                                          reinterpret_cast<__nv_bfloat16*>(dst_hl));
+  HALS_LAUNCH_CHECK();
   return 0;
 }
 

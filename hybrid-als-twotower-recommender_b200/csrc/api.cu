@@ -15,6 +15,8 @@ int als_half_step_tc128(const int32_t* colidx, const float* vals, const float* s
                         float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
 int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* src, int64_t n_src, float* dst,
                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
+int als_half_step_ws128(const int32_t* colidx, const uint32_t* vals_hl, const float* src, int64_t n_src, float* dst,
+                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl, cudaStream_t st);
 int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const float* src, int64_t n_src, float* dst,
                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl, cudaStream_t st);
 int als_launch_split_bf16(const float* src, int64_t n_src, int k, void* out, cudaStream_t st);
@@ -125,12 +127,13 @@ extern "C" int64_t hals_als_plan_chunk_count_host(const int32_t* item_len, int64
 }
 
 extern "C" int hals_als_plan_chunks_host(const int32_t* item_len, const int64_t* item_begin, const int32_t* item_slot,
-                                         int64_t n_items, int64_t* item_chunk0, int64_t* item_cost0, int64_t* chunk_pos,
-                                         int32_t* chunk_cnt) {
+                                         int64_t n_items, int k, int64_t* item_chunk0, int64_t* item_cost0,
+                                         int64_t* chunk_pos, int32_t* chunk_cnt) {
   HALS_REQUIRE(item_len && item_begin && item_slot && item_chunk0 && item_cost0 && chunk_pos && chunk_cnt, "null pointer");
-  // cost of an item in chunk units: its chunks + the solve of a whole row (measured ~6 chunk times with the solvers
-  // of an SM working in parallel) or the parking of a slice's partial sums
-  constexpr int64_t kSolveCost = 6, kParkCost = 2;
+  // cost of an item in chunk units: its chunks + the solve of a whole row (rank 64: measured ~6 chunk times with the
+  // solvers of an SM working in parallel; rank 128: ~8-10k cycles per system against ~300 per chunk) or the parking
+  // of a slice's partial sums
+  const int64_t kSolveCost = k > 64 ? 32 : 6, kParkCost = k > 64 ? 6 : 2;
   int64_t c = 0, cost = 0;
   for (int64_t i = 0; i < n_items; ++i) {
     item_chunk0[i] = c;
@@ -153,18 +156,22 @@ extern "C" int hals_als_split_factors(const float* src, int64_t n_rows, int k, v
   return als_launch_split_bf16(src, n_rows, k, out_hl, (cudaStream_t)stream);
 }
 
-extern "C" int hals_als_half_step_split64(const int32_t* colidx, int64_t m_dst, const void* src_hl, int64_t n_src,
-                                          float* dst, void* dst_hl, float reg, const hals_als_plan* plan,
-                                          void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int hals_als_half_step_split(const int32_t* colidx, int64_t m_dst, const void* src_hl, int64_t n_src,
+                                        float* dst, void* dst_hl, int k, float reg, const hals_als_plan* plan,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
   HALS_REQUIRE(plan != nullptr, "null plan");
+  HALS_REQUIRE(k == 64 || k == 128, "split-form half-steps exist for ranks 64 and 128");
   HALS_REQUIRE(m_dst >= 0 && n_src >= 0, "negative count");
   if (m_dst == 0 || plan->n_items == 0) return 0;
   HALS_REQUIRE(colidx && src_hl && dst && dst_hl, "null pointer");
   HALS_REQUIRE(plan->vals_hl && plan->chunk_pos && plan->chunk_cnt && plan->item_chunk0 && plan->item_cost0,
                "the plan must carry packed ratings and the chunk table");
   HALS_REQUIRE(workspace != nullptr, "null workspace");
-  if (workspace_bytes < slot_region_bytes(plan->n_slots, 64) + 16) return fail(HALS_ERR_WORKSPACE, "%s: workspace too small%s", __func__);
+  if (workspace_bytes < slot_region_bytes(plan->n_slots, k) + 16) return fail(HALS_ERR_WORKSPACE, "%s: workspace too small%s", __func__);
   // rows without ratings are never written: the caller keeps them zero (fp32 and split)
+  if (k == 128)
+    return als_half_step_ws128(colidx, plan->vals_hl, nullptr, n_src, dst, reg, plan, (float*)workspace,
+                               const_cast<void*>(src_hl), dst_hl, (cudaStream_t)stream);
   return als_half_step_ws64(colidx, plan->vals_hl, nullptr, n_src, dst, reg, plan, (float*)workspace,
                             const_cast<void*>(src_hl), dst_hl, (cudaStream_t)stream);
 }
@@ -200,7 +207,13 @@ extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, 
   HALS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
   if (use_tc(k, implicit)) {
     void* split = reinterpret_cast<uint8_t*>(workspace) + slot_region_bytes(plan->n_slots, k);
-    if (k == 128) return als_half_step_tc128(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
+    if (k == 128) {
+      // HALS_TC128_IMPL=groups selects the round-1 kernel (two solver groups, no chunk table)
+      static const bool old128 = [] { const char* e = getenv("HALS_TC128_IMPL"); return e && e[0] == 'g'; }();
+      if (old128 || plan->vals_hl == nullptr || plan->chunk_pos == nullptr)
+        return als_half_step_tc128(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
+      return als_half_step_ws128(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split, nullptr, st);
+    }
     // HALS_TC64_IMPL=cta4 selects the round-1 kernel (four 4-warp CTAs per SM); default: warp-specialised kernel
     static const bool old64 = [] { const char* e = getenv("HALS_TC64_IMPL"); return e && e[0] == 'c'; }();
     if (old64 || plan->vals_hl == nullptr || plan->chunk_pos == nullptr)

@@ -101,8 +101,8 @@ int hals_als_plan_fill_host(const int64_t* rowptr_host, int64_t m, int32_t seg_l
  * the number of chunks, or -1 on invalid input. */
 int64_t hals_als_plan_chunk_count_host(const int32_t* item_len, int64_t n_items);
 int hals_als_plan_chunks_host(const int32_t* item_len, const int64_t* item_begin, const int32_t* item_slot,
-                              int64_t n_items, int64_t* item_chunk0, int64_t* item_cost0, int64_t* chunk_pos,
-                              int32_t* chunk_cnt);
+                              int64_t n_items, int k /* rank: sets the solve : gather cost ratio */,
+                              int64_t* item_chunk0, int64_t* item_cost0, int64_t* chunk_pos, int32_t* chunk_cnt);
 /* Bytes of device workspace hals_als_half_step needs for a plan with n_slots slots and a
  * source factor matrix of n_src rows (the tensor-core path keeps a bf16 split copy of it). */
 size_t hals_als_workspace_bytes(int64_t n_slots, int k, int64_t n_src);
@@ -117,18 +117,18 @@ int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, const float
                        const hals_als_plan* plan /* device arrays inside */, void* workspace,
                        size_t workspace_bytes, void* stream);
 
-/* Rank 64, factors kept in split form across half-steps (what als_engine does; the stateless call above re-splits
+/* Ranks 64 and 128, factors kept in split form across half-steps (what als_engine does; the stateless call above re-splits
  * the whole source matrix every time, which is a replicated pass on every rank of a sharded run).
  *   hals_als_split_factors: out_hl[r] = [bf16(x) (k) | bf16(x - bf16(x)) (k)] for n_rows rows (k = 64 or 128).
- *   hals_als_half_step_split64: src_hl = split source factors, [n_src + 1] rows of 128 bf16, ROW n_src ALL ZERO (the
- *     ragged tail of a chunk gathers it); every solved row j is written twice: dst[j] (fp32, 64) and dst_hl[j] (its
- *     split, 128 bf16) -- dst and dst_hl are indexed by the plan's destination rows.  Rows without ratings are not
+ *   hals_als_half_step_split: src_hl = split source factors, [n_src + 1] rows of 2k bf16, ROW n_src ALL ZERO (the
+ *     ragged tail of a chunk gathers it); every solved row j is written twice: dst[j] (fp32, k) and dst_hl[j] (its
+ *     split, 2k bf16) -- dst and dst_hl are indexed by the plan's destination rows.  Rows without ratings are not
  *     touched.  colidx indexes rows of src_hl (a sharded engine stores the factors padded by owner rank, so that the
  *     all-gather of the freshly solved rows is in place, and remaps colidx once).  Explicit feedback only. */
 int hals_als_split_factors(const float* src, int64_t n_rows, int k, void* out_hl, void* stream);
-int hals_als_half_step_split64(const int32_t* colidx, int64_t m_dst, const void* src_hl, int64_t n_src, float* dst,
-                               void* dst_hl, float reg, const hals_als_plan* plan, void* workspace,
-                               size_t workspace_bytes, void* stream);
+int hals_als_half_step_split(const int32_t* colidx, int64_t m_dst, const void* src_hl, int64_t n_src, float* dst,
+                             void* dst_hl, int k, float reg, const hals_als_plan* plan, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* Dense Gram Y^T Y ([n,k] -> [k,k], fp32 out).  Replaces Spark's computeYtY (implicit
  * mode) behind src/als_model.py:62.  workspace: hals_gram_workspace_bytes(k). */

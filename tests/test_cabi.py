@@ -79,7 +79,7 @@ def test_chunk_table_matches_the_items():
     assert nch == int(((ln + 31) // 32).sum())
     c0, cost0 = np.empty(ni + 1, np.int64), np.empty(ni + 1, np.int64)
     pos, cnt = np.empty(nch, np.int64), np.empty(nch, np.int32)
-    nat.check(L.hals_als_plan_chunks_host(nat.ptr(ln), nat.ptr(beg), nat.ptr(slot), ni, nat.ptr(c0), nat.ptr(cost0),
+    nat.check(L.hals_als_plan_chunks_host(nat.ptr(ln), nat.ptr(beg), nat.ptr(slot), ni, 64, nat.ptr(c0), nat.ptr(cost0),
                                           nat.ptr(pos), nat.ptr(cnt)))
     assert c0[0] == 0 and c0[-1] == nch and (np.diff(c0) == (ln + 31) // 32).all()
     assert cost0[0] == 0 and (np.diff(cost0) > 0).all()
