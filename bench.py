@@ -34,6 +34,10 @@ WORKLOADS = {
                desc="MovieLens-20M shape 138,493 x 26,744, 20,000,263 ratings, explicit ALS rank 64"),
     "c3": dict(users=480_189, items=17_770, nnz=100_480_507, rank=128, reg=0.1, half=False,
                desc="Netflix-prize shape 480,189 x 17,770, 100,480,507 ratings, explicit ALS rank 128"),
+    # config 4 is quoted on 8 GPUs (10M users x 1M items, 1e9 interactions): one GPU's share of it -- 1/8 of the users
+    # and interactions against the full item catalogue; N GPUs run N shares (weak scaling up to the full shape at 8)
+    "c4s": dict(users=1_250_000, items=1_000_000, nnz=125_000_000, rank=128, reg=0.1, half=False, implicit=True, alpha=40.0,
+                desc="1/8 slice per GPU of the implicit-feedback shape 10M x 1M, 1e9 interactions, Hu-Koren ALS rank 128"),
 }
 METRIC = "als_ratings_per_sec_per_sweep"
 UNIT = "ratings/s"
@@ -396,17 +400,21 @@ def scoring_leg(args, dev, rank, world, barrier):
             "users_rerun_exactly_first_slab": flagged}
 
 
-def c3_leg(args, dev, rank, world, barrier):
-    """BASELINE config 3 (Netflix-prize shape, rank 128) at every N the driver runs: sweep time only (device events,
-    max over ranks), same synthetic generator, same sharding as the headline workload."""
+def c3_leg(args, dev, rank, world, barrier, name="c3"):
+    """BASELINE config 3 (Netflix-prize shape, rank 128) or the config-4 slice (name="c4s": implicit feedback, users and
+    interactions grow with N) at every N the driver runs: sweep time only (device events, max over ranks), same
+    synthetic generator, same sharding as the headline workload."""
     import torch
     import torch.distributed as dist
     from hybrid_als_twotower_recommender_b200.als_engine import AlsEngine
-    w = WORKLOADS["c3"]
+    w = dict(WORKLOADS[name])
+    if name == "c4s":
+        w["users"], w["nnz"] = w["users"] * world, w["nnz"] * world
     u, i, r = synth_coo(w, dev)
     data_sum = coo_checksum(u, i, r)
-    eng = AlsEngine(u, i, r, w["users"], w["items"], w["rank"], w["reg"], device=dev, dist_rank=rank, world=world)
-    assert_same_on_all_ranks([data_sum] + list(eng.user_bounds) + list(eng.item_bounds), "c3 inputs / shard bounds", dev, world)
+    eng = AlsEngine(u, i, r, w["users"], w["items"], w["rank"], w["reg"], implicit=bool(w.get("implicit")),
+                    alpha=float(w.get("alpha", 1.0)), device=dev, dist_rank=rank, world=world)
+    assert_same_on_all_ranks([data_sum] + list(eng.user_bounds) + list(eng.item_bounds), f"{name} inputs / shard bounds", dev, world)
     del u, i, r
     eng.init_user_factors(1)
     eng.enable_graphs()
@@ -426,7 +434,8 @@ def c3_leg(args, dev, rank, world, barrier):
     b_item, b_user = algorithmic_bytes(w)
     peak, _ = measured_peaks()
     out = {"metric": METRIC, "value": w["nnz"] / (ms * 1e-3), "unit": UNIT, "ms_per_sweep": ms, "steps": args.c3_steps,
-           "workload": f"c3: {w['desc']}", "n_gpus": world, "inputs_checksum": data_sum,
+           "workload": f"{name}: {w['desc']}", "n_gpus": world, "inputs_checksum": data_sum,
+           "users": w["users"], "items": w["items"], "nnz": w["nnz"], "scaling": "weak" if name == "c4s" else "strong",
            "roofline_frac": (b_item + b_user) / world / (ms * 1e-3) / 1e9 / peak,
            "algorithmic_bytes_per_sweep": b_item + b_user}
     del eng
@@ -451,6 +460,7 @@ def main():
     ap.add_argument("--no-scoring", action="store_true", help="skip the hybrid top-k scoring leg (extra.hybrid_topk)")
     ap.add_argument("--no-c3", action="store_true", help="skip the config-3 sweep timing (extra.als_c3)")
     ap.add_argument("--c3-steps", type=int, default=3)
+    ap.add_argument("--no-c4", action="store_true", help="skip the config-4 slice (implicit feedback) sweep timing (extra.als_c4_slice)")
     ap.add_argument("--score-users", type=int, default=1_000_000)
     ap.add_argument("--score-slab", type=int, default=65536)
     ap.add_argument("--score-items-per-gpu", type=int, default=1_250_000)
@@ -576,6 +586,9 @@ def main():
     c3_extra = None
     if not args.no_c3:
         c3_extra = c3_leg(args, dev, rank, world, barrier)
+    c4_extra = None
+    if not args.no_c4:
+        c4_extra = c3_leg(args, dev, rank, world, barrier, name="c4s")
 
     scoring_extra = None
     if not args.no_scoring:
@@ -630,6 +643,8 @@ def main():
         extra["hybrid_topk"] = scoring_extra
     if c3_extra is not None:
         extra["als_c3"] = c3_extra
+    if c4_extra is not None:
+        extra["als_c4_slice"] = c4_extra
     if extra:
         line["extra"] = extra
     line["config"]["inputs_checksum"] = data_sum

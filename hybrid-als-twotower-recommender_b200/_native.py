@@ -30,7 +30,7 @@ class AlsPlan(ctypes.Structure):
         ("long_row", c_vp), ("long_slot0", c_vp), ("long_nseg", c_vp),
         ("n_long_gt16", c_i64), ("n_long_gt256", c_i64),
         ("n_chunks", c_i64), ("item_chunk0", c_vp), ("item_cost0", c_vp), ("chunk_pos", c_vp), ("chunk_cnt", c_vp),
-        ("vals_hl", c_vp),
+        ("vals_hl", c_vp), ("vals_scale", c_vp), ("item_npos", c_vp), ("packed_alpha", c_f32),
     ]
 
 
@@ -59,6 +59,8 @@ SIGNATURES = {
     "hals_als_workspace_bytes": (c_sz, [c_i64, ctypes.c_int, c_i64]),
     "hals_als_default_seg_len": (c_i32, [ctypes.c_int]),
     "hals_als_pack_ratings": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "hals_als_pack_ratings_implicit": (ctypes.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
+    "hals_als_plan_count_positive": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "hals_als_half_step": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, ctypes.c_int, c_f32,
                                           ctypes.c_int, c_f32, c_vp, ctypes.POINTER(AlsPlan), c_vp, c_sz, c_vp]),
     "hals_als_split_factors": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_vp, c_vp]),

@@ -207,8 +207,8 @@ class AlsEngine:
         _mark("routing + CSR build")
         self.plan_R = self.plan_Rt = None
         if make_plans:
-            self.plan_R = AlsPlanHandle(self.R, self.k, seg_len, n_src=n_items)
-            self.plan_Rt = AlsPlanHandle(self.Rt, self.k, seg_len, n_src=n_users)
+            self.plan_R = AlsPlanHandle(self.R, self.k, seg_len, n_src=n_items, implicit=self.implicit, alpha=self.alpha)
+            self.plan_Rt = AlsPlanHandle(self.Rt, self.k, seg_len, n_src=n_users, implicit=self.implicit, alpha=self.alpha)
         _mark("work plans")
         self.X = torch.zeros((n_users, self.k), dtype=torch.float32, device=self.device)
         self.Y = torch.zeros((n_items, self.k), dtype=torch.float32, device=self.device)

@@ -85,7 +85,8 @@ def build_csr(rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n_rows
 class AlsPlanHandle:
     """Owns the device arrays of a hals_als_plan and the matching workspace."""
 
-    def __init__(self, shard: CsrShard, k: int, seg_len: int | None = None, device=None, n_src: int = 0):
+    def __init__(self, shard: CsrShard, k: int, seg_len: int | None = None, device=None, n_src: int = 0,
+                 implicit: bool = False, alpha: float = 1.0):
         L = nat.lib()
         self.k = k
         rp = np.ascontiguousarray(shard.rowptr_host, dtype=np.int64)
@@ -152,8 +153,22 @@ class AlsPlanHandle:
         dev = device if device is not None else shard.colidx.device
         self.dev = {n: torch.from_numpy(a).to(dev) for n, a in h.items()}
         # ratings as bf16 hi|lo pairs, packed once: the tensor-core kernels copy them into its operand
-        self.vals_hl = None
-        if k in (64, 128) and torch.device(dev).type == "cuda" and shard.vals.numel() > 0:
+        # (implicit feedback, rank 128: the Hu-Koren operands -- see hals_als_plan.vals_scale in include/hals_b200.h)
+        self.vals_hl = self.vals_scale = self.item_npos = None
+        self.packed_alpha = 0.0
+        on_gpu = torch.device(dev).type == "cuda" and shard.vals.numel() > 0
+        if implicit and k == 128 and on_gpu and alpha > 0 and self.n_items > 0:
+            nnz = shard.vals.numel()
+            self.vals_hl = torch.empty(nnz, dtype=torch.int32, device=dev)
+            self.vals_scale = torch.empty(nnz, dtype=torch.float32, device=dev)
+            self.item_npos = torch.empty(self.n_items, dtype=torch.int32, device=dev)
+            nat.check(L.hals_als_pack_ratings_implicit(nat.ptr(shard.vals), nnz, float(alpha), nat.ptr(self.vals_hl),
+                                                       nat.ptr(self.vals_scale), nat.current_stream()), "pack_ratings_implicit")
+            nat.check(L.hals_als_plan_count_positive(nat.ptr(shard.vals), nat.ptr(self.dev["item_begin"]),
+                                                     nat.ptr(self.dev["item_len"]), self.n_items, nat.ptr(self.item_npos),
+                                                     nat.current_stream()), "plan_count_positive")
+            self.packed_alpha = float(np.float32(alpha))
+        elif not implicit and k in (64, 128) and on_gpu:
             self.vals_hl = torch.empty(shard.vals.numel(), dtype=torch.int32, device=dev)
             nat.check(L.hals_als_pack_ratings(nat.ptr(shard.vals), shard.vals.numel(), nat.ptr(self.vals_hl),
                                               nat.current_stream()), "hals_als_pack_ratings")
@@ -161,6 +176,8 @@ class AlsPlanHandle:
             n_items=self.n_items, n_long_rows=self.n_long, n_slots=self.n_slots, seg_len=self.seg_len,
             max_nseg=int(h["long_nseg"][: self.n_long].max()) if self.n_long else 0,
             vals_hl=self.vals_hl.data_ptr() if self.vals_hl is not None else None, n_chunks=self.n_chunks,
+            vals_scale=self.vals_scale.data_ptr() if self.vals_scale is not None else None,
+            item_npos=self.item_npos.data_ptr() if self.item_npos is not None else None, packed_alpha=self.packed_alpha,
             n_long_gt16=n_gt16 if self.n_long else 0, n_long_gt256=n_gt256 if self.n_long else 0,
             **{n: self.dev[n].data_ptr() for n in h})
         self.workspace_bytes = int(L.hals_als_workspace_bytes(self.n_slots, k, int(n_src)))

@@ -473,7 +473,8 @@ als_tc128_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ v
 __global__ void __launch_bounds__(128)
 als_reduce_solve128_kernel(const float* __restrict__ workspace, float* __restrict__ dst, float reg,
                            const int32_t* __restrict__ long_row, const int32_t* __restrict__ long_slot0,
-                           const int32_t* __restrict__ long_nseg, int slot_group, __nv_bfloat16* __restrict__ dst_hl) {
+                           const int32_t* __restrict__ long_nseg, int slot_group, __nv_bfloat16* __restrict__ dst_hl,
+                           const float* __restrict__ gram) {
   constexpr int K = k8K;
   __shared__ __align__(16) float PS[2 * k8LDP + 128];
   const int m = threadIdx.x;
@@ -495,6 +496,13 @@ als_reduce_solve128_kernel(const float* __restrict__ workspace, float* __restric
     cnt += W[K * K + K];
   }
   const float lam = reg * cnt;
+  if (gram != nullptr) {                                   // implicit feedback: + Y^T Y (row m of the symmetric matrix)
+#pragma unroll
+    for (int n = 0; n < 128; n += 4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gram + m * K + n));
+      a[n] += g.x; a[n + 1] += g.y; a[n + 2] += g.z; a[n + 3] += g.w;
+    }
+  }
   f32x2 ap[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i)
@@ -529,7 +537,7 @@ int als_half_step_tc128(const int32_t* colidx, const float* vals, const float* s
     constexpr int kGroup = 16;                            // == kSlotGroup of als_tc.cu
     if (int rc = als_launch_slot_group_sum(slots, plan, (int)k8SlotFloats, st)) return rc;
     als_reduce_solve128_kernel<<<(unsigned)plan->n_long_rows, 128, 0, st>>>(slots, dst, reg, plan->long_row,
-                                                                            plan->long_slot0, plan->long_nseg, kGroup, nullptr);
+                                                                            plan->long_slot0, plan->long_nseg, kGroup, nullptr, nullptr);
     HALS_LAUNCH_CHECK();
   }
   return 0;
@@ -537,10 +545,10 @@ int als_half_step_tc128(const int32_t* colidx, const float* vals, const float* s
 
 // the long-row tail of the warp-specialised kernel (als_ws128.cu); the slot groups are already pre-summed
 int als_launch_reduce_solve128(const float* slots, float* dst, float reg, const hals_als_plan* plan, void* dst_hl,
-                               cudaStream_t st) {
+                               const float* gram, cudaStream_t st) {
   als_reduce_solve128_kernel<<<(unsigned)plan->n_long_rows, 128, 0, st>>>(slots, dst, reg, plan->long_row, plan->long_slot0,
                                                                           plan->long_nseg, 16,
-                                                                          reinterpret_cast<__nv_bfloat16*>(dst_hl));
+                                                                          reinterpret_cast<__nv_bfloat16*>(dst_hl), gram);
   HALS_LAUNCH_CHECK();
   return 0;
 }

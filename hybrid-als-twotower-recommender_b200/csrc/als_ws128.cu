@@ -14,6 +14,11 @@
 //                    group's register tile A = C + C^T, release the hand-over matrix, solve.  Groups take rows
 //                    round-robin: drain + tile load are serialised through the single hand-over matrix
 //                    (~3.5k cycles per row), the 128-pivot eliminations of three rows overlap.
+//   Implicit feedback (Hu-Koren, Spark implicitPrefs): A = Y^T Y + sum c y y^T + lambda n+ I, b = sum_{r>0} (1 + c) y with
+//   c = alpha |r|.  Warp 15 rescales every landed stage in place, row t by sqrt(c_t) (s = sqrt(c) (h + l) in fp32, re-split
+//   into bf16 hi/lo), so the SAME three MMAs build sum c y y^T; the rating column carries (1 + c) / sqrt(c) (0 unless
+//   r > 0), so H^T R is b; the Gram matrix, permuted once per half-step into the solver's lane-tile order, is added when a
+//   group loads its tile; n+ (ratings > 0 per work item) comes with the plan.
 //   Solver = the one-tile-per-lane L D L^T of als_ws64.cu on 128 lanes: lane (ti = 0..7, tj = 0..15) owns rows
 //   {ti + 16q, ti + 8 + 16q} x columns {tj + 16c} of the lower triangle (36 packed fp32x2), pivot columns go through
 //   a 512-byte buffer, ONE named barrier of the group per pivot.  (The round-1 kernel, als_tc128.cu: two groups, full
@@ -53,6 +58,7 @@ static_assert(kStages % 2 == 0, "the two gather warps own alternate stages");
 
 struct Bars {
   uint64_t st_full[kStages], st_free[kStages];
+  uint64_t st_scaled[kStages];     // implicit mode: stage rescaled by sqrt(c) (what the MMA warp then waits for)
   uint64_t acc_full[kGroups];      // accumulator of a row complete, per destination group (a waiter may lag one phase)
   uint64_t acc_free;               // accumulator drained (128 arrivals of the draining group)
   uint64_t c_turn[kGroups];        // hand-over matrix free for group g's next row (arrival by the group before it)
@@ -95,7 +101,7 @@ __device__ __forceinline__ void cp_async16_raw(uint32_t smem_dst, uint64_t gsrc)
 // ---- G: gather (see als_ws64.cu for the scheme; here one warp instruction copies one 512-byte row) -------------
 __device__ __noinline__ void gather_role(uint32_t stages, Bars* bars, uint8_t* gscratch, const Range* rg,
                                          const int32_t* __restrict__ colidx, const uint32_t* __restrict__ vals_hl,
-                                         const uint8_t* __restrict__ src_hl, int zero_row,
+                                         const float* __restrict__ vals_sc, const uint8_t* __restrict__ src_hl, int zero_row,
                                          const int64_t* __restrict__ chunk_pos, const int32_t* __restrict__ chunk_cnt,
                                          int gw, int lane) {
   const uint32_t ring = umma::smem_u32(gscratch);                       // int  [2][kBurst][32]
@@ -144,6 +150,7 @@ __device__ __noinline__ void gather_role(uint32_t stages, Bars* bars, uint8_t* g
   for (int i = 0; i < 8; ++i) dsto[i] = (uint32_t)(lane >> 3) * kBlk + (uint32_t)(((lane & 7) ^ i) << 4);
   const uint64_t srcb = reinterpret_cast<uint64_t>(src_hl) + (uint64_t)lane * 16u;
   const uint32_t rdst = 4 * kBlk + (uint32_t)lane * kRowBytes + (uint32_t)((lane & 7) << 4);
+  const uint32_t sdst = 4 * kBlk + (uint32_t)lane * kRowBytes + (uint32_t)((7 ^ (lane & 7)) << 4);   // a chunk no MMA reads
   uint32_t s = (uint32_t)gw, u = 0;
   fill(0);
   stash(0);
@@ -177,6 +184,10 @@ __device__ __noinline__ void gather_role(uint32_t stages, Bars* bars, uint8_t* g
         const bool ok = lane < cnt;
         const uint32_t* rp = vals_hl + pos + (ok ? lane : 0);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(st + rdst), "l"(rp), "r"(ok ? 4 : 0) : "memory");
+        if (vals_sc != nullptr) {
+          const float* sp = vals_sc + pos + (ok ? lane : 0);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(st + sdst), "l"(sp), "r"(ok ? 4 : 0) : "memory");
+        }
       }
       cp_async_mbar_arrive_noinc(&bars->st_full[s]);
       s += 2;
@@ -188,9 +199,56 @@ __device__ __noinline__ void gather_role(uint32_t stages, Bars* bars, uint8_t* g
   }
 }
 
+// ---- implicit mode: rescale a landed stage in place, row t (= lane) by sqrt(c_t) ------------------------------------
+__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ f32x2 unpack_bf16x2(uint32_t w) {             // (element 0, element 1) as fp32
+  return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __noinline__ void scaler_role(uint32_t stages, Bars* bars, const Range* rg, const int32_t* __restrict__ chunk_cnt,
+                                         int lane) {
+  const int64_t k_lo = rg->chunk_lo, k_hi = rg->chunk_hi;
+  const uint32_t rowo = (uint32_t)lane * kRowBytes, x = (uint32_t)(lane & 7);
+  const f32x2 one2 = pack2(1.f, 1.f), mone2 = pack2(-1.f, -1.f);
+  uint32_t s = 0, su = 0;
+  for (int64_t k = k_lo; k < k_hi; ++k) {
+    umma::mbar_wait(&bars->st_full[s], su & 1);
+    const uint32_t st = stages + s * kStageBytes;
+    const float sc = lds32(st + 4 * kBlk + rowo + ((7u ^ x) << 4));
+    const f32x2 sc2 = pack2(sc, sc);
+#pragma unroll 2
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t off = st + (uint32_t)(i >> 3) * kBlk + rowo + ((((uint32_t)i & 7u) ^ x) << 4);
+      const float4 hv = lds128(off), lv = lds128(off + 2 * kBlk);
+      const uint32_t hw[4] = {__float_as_uint(hv.x), __float_as_uint(hv.y), __float_as_uint(hv.z), __float_as_uint(hv.w)};
+      const uint32_t lw[4] = {__float_as_uint(lv.x), __float_as_uint(lv.y), __float_as_uint(lv.z), __float_as_uint(lv.w)};
+      uint32_t oh[4], ol[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const f32x2 y = ffma2(unpack_bf16x2(hw[j]), one2, unpack_bf16x2(lw[j]));
+        const f32x2 v = fmul2(y, sc2);
+        oh[j] = cvt_bf16x2(hi2(v), lo2(v));
+        const f32x2 r = ffma2(unpack_bf16x2(oh[j]), mone2, v);
+        ol[j] = cvt_bf16x2(hi2(r), lo2(r));
+      }
+      sts128(off, __uint_as_float(oh[0]), __uint_as_float(oh[1]), __uint_as_float(oh[2]), __uint_as_float(oh[3]));
+      sts128(off + 2 * kBlk, __uint_as_float(ol[0]), __uint_as_float(ol[1]), __uint_as_float(ol[2]), __uint_as_float(ol[3]));
+    }
+    umma::fence_proxy_async();                      // generic-proxy writes -> the tensor core's async-proxy reads
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(&bars->st_scaled[s]);
+    if (++s == (uint32_t)kStages) { s = 0; ++su; }
+  }
+  (void)chunk_cnt;
+}
+
 // ---- M: MMA issue --------------------------------------------------------------------------------------------
 __device__ __noinline__ void mma_role(uint32_t sbase, uint32_t tmem, Bars* bars, const Range* rg,
-                                      const int32_t* __restrict__ chunk_cnt, int lane) {
+                                      const int32_t* __restrict__ chunk_cnt, bool scaled, int lane) {
+  uint64_t* const ready = scaled ? bars->st_scaled : bars->st_full;
   constexpr uint32_t idesc256 = umma::make_instr_desc(umma::kFmtBF16, true, true, 128, 256);
   constexpr uint32_t idesc16 = umma::make_instr_desc(umma::kFmtBF16, true, true, 128, 16);
   const int64_t k_lo = rg->chunk_lo, k_hi = rg->chunk_hi;
@@ -212,7 +270,7 @@ __device__ __noinline__ void mma_role(uint32_t sbase, uint32_t tmem, Bars* bars,
           if (row > 0) umma::mbar_wait(&bars->acc_free, (row - 1) & 1);     // the previous row has left TMEM
           umma::fence_after_sync();
         }
-        umma::mbar_wait(&bars->st_full[s], su & 1);
+        umma::mbar_wait(&ready[s], su & 1);
         const uint64_t so = (uint64_t)((s * kStageBytes) >> 4);
 #pragma unroll
         for (int ks = 0; ks < KC / 16; ++ks) {
@@ -387,7 +445,7 @@ __device__ __noinline__ void solver_role(uint32_t sC, uint32_t scratch, uint32_t
                                          float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_hl,
                                          float* __restrict__ workspace, float reg, const int32_t* __restrict__ item_row,
                                          const int32_t* __restrict__ item_len, const int32_t* __restrict__ item_slot,
-                                         const Range* rg, int group, int gl) {
+                                         const float* __restrict__ gram_tiles, const Range* rg, int group, int gl) {
   const int ti = gl & 7, tj = gl >> 3;
   const int bar = 1 + group;
   const uint32_t sB = sC + 128 * kLdc * 4;
@@ -463,6 +521,15 @@ __device__ __noinline__ void solver_role(uint32_t sC, uint32_t scratch, uint32_t
           R[tri(q, c)] = pack2(a[0], a[1]);
         }
       }
+      if (gram_tiles != nullptr) {                           // implicit: + Y^T Y, already in this lane's tile order
+        const float4* gp = reinterpret_cast<const float4*>(gram_tiles) + gl * 18;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+          const float4 g = __ldg(gp + i);
+          R[2 * i] = ffma2(pack2(g.x, g.y), pack2(1.f, 1.f), R[2 * i]);
+          R[2 * i + 1] = ffma2(pack2(g.z, g.w), pack2(1.f, 1.f), R[2 * i + 1]);
+        }
+      }
       const uint32_t ob = (uint32_t)(ti + 16 * (tj & 7)) * 4u;
       bb2 = tj < 8 ? pack2(lds32(sB + ob), lds32(sB + ob + 32)) : 0ull;
       group_sync(bar);
@@ -517,6 +584,7 @@ __device__ __noinline__ void solver_role(uint32_t sC, uint32_t scratch, uint32_t
 
 __global__ void __launch_bounds__(kThreads, 1)
 als_ws128_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict__ vals_hl,
+                 const float* __restrict__ vals_sc, const float* __restrict__ gram_tiles,
                  const __nv_bfloat16* __restrict__ src_hl, float* __restrict__ dst, float reg,
                  const int32_t* __restrict__ item_row, const int32_t* __restrict__ item_len,
                  const int32_t* __restrict__ item_slot, const int64_t* __restrict__ item_chunk0,
@@ -531,7 +599,11 @@ als_ws128_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
   if (tid == 32) {
-    for (int s = 0; s < kStages; ++s) { umma::mbar_init(&bars.st_full[s], 32); umma::mbar_init(&bars.st_free[s], 1); }
+    for (int s = 0; s < kStages; ++s) {
+      umma::mbar_init(&bars.st_full[s], 32);
+      umma::mbar_init(&bars.st_free[s], 1);
+      umma::mbar_init(&bars.st_scaled[s], 1);
+    }
     for (int g = 0; g < kGroups; ++g) { umma::mbar_init(&bars.acc_full[g], 1); umma::mbar_init(&bars.c_turn[g], 1); }
     umma::mbar_init(&bars.acc_free, 128);
     umma::mbar_fence_init();
@@ -565,13 +637,14 @@ als_ws128_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict_
   if (warp < 4 * kGroups) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kRegsSolver));
     solver_role(sC, scratch + (uint32_t)(warp >> 2) * kGroupScratch, tmem, &bars, dst, dst_hl, workspace, reg, item_row,
-                item_len, item_slot, &range, warp >> 2, tid & 127);
+                item_len, item_slot, gram_tiles, &range, warp >> 2, tid & 127);
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kRegsFront));
     if (warp < kWarpMma)
-    gather_role(sbase, &bars, gscratch + (warp - kWarpGather) * kGatherScratch, &range, colidx, vals_hl,
+    gather_role(sbase, &bars, gscratch + (warp - kWarpGather) * kGatherScratch, &range, colidx, vals_hl, vals_sc,
                 reinterpret_cast<const uint8_t*>(src_hl), zero_row, chunk_pos, chunk_cnt, warp - kWarpGather, lane);
-    else if (warp == kWarpMma) mma_role(sbase, tmem, &bars, &range, chunk_cnt, lane);
+    else if (warp == kWarpMma) mma_role(sbase, tmem, &bars, &range, chunk_cnt, vals_sc != nullptr, lane);
+    else if (vals_sc != nullptr) scaler_role(sbase, &bars, &range, chunk_cnt, lane);
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -580,22 +653,41 @@ als_ws128_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict_
 
 }  // namespace ws128
 
+// Y^T Y ([128][128], symmetric) -> the solver's lane-tile order: tiles[gl][tri(q, c)] = (G[ti + 16q][tj + 16c],
+// G[ti + 8 + 16q][tj + 16c]) with gl = ti + 8 tj -- a lane adds its share with 18 contiguous 16-byte loads.
+__global__ void gram_to_tiles128_kernel(const float* __restrict__ G, float* __restrict__ tiles) {
+  const int gl = threadIdx.x, ti = gl & 7, tj = gl >> 3;
+  for (int q = 0; q < 8; ++q)
+    for (int c = 0; c <= q; ++c)
+      for (int h = 0; h < 2; ++h)
+        tiles[gl * 72 + ws128::tri(q, c) * 2 + h] = G[(ti + 8 * h + 16 * q) * ws128::K + tj + 16 * c];
+}
+
 int als_launch_slot_group_sum(float* slots, const hals_als_plan* plan, int slot_floats, cudaStream_t st);   // als_tc.cu
 int als_launch_reduce_solve128(const float* slots, float* dst, float reg, const hals_als_plan* plan, void* dst_hl,
-                               cudaStream_t st);                                                             // als_tc128.cu
+                               const float* gram, cudaStream_t st);                                          // als_tc128.cu
 
 // src != nullptr: fp32 source factors, split into `split_buf` first.  src == nullptr: `split_buf` already holds the
 // split source ([n_src + 1][256] bf16, row n_src all zero); see als_half_step_ws64.
+// gram != nullptr selects implicit feedback: the plan must carry vals_scale / item_npos (packed for the caller's alpha),
+// `gram_tiles` is 36,864 bytes of scratch.
 int als_half_step_ws128(const int32_t* colidx, const uint32_t* vals_hl, const float* src, int64_t n_src, float* dst,
-                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl, cudaStream_t st) {
+                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl,
+                        const float* gram, float* gram_tiles, cudaStream_t st) {
   using namespace ws128;
   __nv_bfloat16* hl = reinterpret_cast<__nv_bfloat16*>(split_buf);
-  HALS_REQUIRE(n_src < (int64_t)1 << 23, "rank-128 kernel: at most 2^23 source rows");
+  HALS_REQUIRE(n_src < (int64_t)1 << 31, "at most 2^31 - 1 source rows");
   if (src != nullptr) {
     const int64_t nthreads = n_src * (K / 8);
     split_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(src, n_src, K, hl);
     HALS_LAUNCH_CHECK();
     HALS_CUDA(cudaMemsetAsync(hl + (size_t)n_src * 2 * K, 0, 4 * K, st));
+  }
+  const bool implicit = gram != nullptr;
+  if (implicit) {
+    HALS_REQUIRE(plan->vals_scale && plan->item_npos && gram_tiles, "implicit mode needs the plan's vals_scale / item_npos");
+    gram_to_tiles128_kernel<<<1, 128, 0, st>>>(gram, gram_tiles);
+    HALS_LAUNCH_CHECK();
   }
   const size_t smem = (size_t)kStages * kStageBytes + kCBytes + (size_t)kGroups * kGroupScratch + 2 * kGatherScratch + 1024;
   static_assert(kStages * kStageBytes + kCBytes + kGroups * kGroupScratch + 2 * kGatherScratch + 1024 <= 227 * 1024 - 1024,
@@ -606,14 +698,15 @@ int als_half_step_ws128(const int32_t* colidx, const uint32_t* vals_hl, const fl
     return fail(HALS_ERR_CUDA, "%s: als_ws128_kernel was compiled for an unexpected register count%s", __func__);
   int64_t grid = sm_count();
   if (grid > plan->n_items) grid = plan->n_items;
-  als_ws128_kernel<<<(unsigned)grid, kThreads, smem, st>>>(colidx, vals_hl, hl, dst, reg, plan->item_row, plan->item_len,
-                                                          plan->item_slot, plan->item_chunk0, plan->item_cost0,
+  als_ws128_kernel<<<(unsigned)grid, kThreads, smem, st>>>(colidx, vals_hl, implicit ? plan->vals_scale : nullptr,
+                                                          implicit ? gram_tiles : nullptr, hl, dst, reg, plan->item_row,
+                                                          implicit ? plan->item_npos : plan->item_len, plan->item_slot, plan->item_chunk0, plan->item_cost0,
                                                           plan->chunk_pos, plan->chunk_cnt, plan->n_items, (int)n_src, slots,
                                                           reinterpret_cast<__nv_bfloat16*>(dst_hl));
   HALS_LAUNCH_CHECK();
   if (plan->n_long_rows > 0) {
     if (int rc = als_launch_slot_group_sum(slots, plan, (int)kSlotFloats, st)) return rc;
-    if (int rc = als_launch_reduce_solve128(slots, dst, reg, plan, dst_hl, st)) return rc;
+    if (int rc = als_launch_reduce_solve128(slots, dst, reg, plan, dst_hl, gram, st)) return rc;
   }
   return 0;
 }

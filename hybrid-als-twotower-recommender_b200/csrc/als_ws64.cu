@@ -747,6 +747,50 @@ int als_pack_ratings(const float* vals, int64_t nnz, uint32_t* out, cudaStream_t
   return 0;
 }
 
+// Implicit feedback (Hu-Koren, c = alpha |r|): the tensor-core kernel rescales gathered rows by sqrt(c) and takes the
+// right-hand side from a rating column that holds (1 + c) / sqrt(c) where r > 0 and 0 elsewhere:
+//   sum (sqrt(c) y)(sqrt(c) y)^T = sum c y y^T,   sum (sqrt(c) y) (1 + c) / sqrt(c) = sum_{r>0} (1 + c) y.
+__global__ void pack_ratings_implicit_kernel(const float* __restrict__ vals, int64_t nnz, float alpha,
+                                             uint32_t* __restrict__ out_hl, float* __restrict__ out_scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const float r = vals[i];
+  const float c = alpha * fabsf(r);
+  const float sc = sqrtf(c);
+  const float rho = r > 0.f && c > 0.f ? (1.f + c) / sc : 0.f;
+  const __nv_bfloat16 rh = __float2bfloat16_rn(rho);
+  const __nv_bfloat16 rl = __float2bfloat16_rn(rho - __bfloat162float(rh));
+  out_hl[i] = (uint32_t)__bfloat16_as_ushort(rh) | ((uint32_t)__bfloat16_as_ushort(rl) << 16);
+  out_scale[i] = sc;
+}
+
+int als_pack_ratings_implicit(const float* vals, int64_t nnz, float alpha, uint32_t* out_hl, float* out_scale, cudaStream_t st) {
+  pack_ratings_implicit_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(vals, nnz, alpha, out_hl, out_scale);
+  HALS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ratings > 0 of every work item (one warp per item): the n of Spark's lambda * n in implicit mode
+__global__ void count_positive_kernel(const float* __restrict__ vals, const int64_t* __restrict__ item_begin,
+                                      const int32_t* __restrict__ item_len, int64_t n_items, int32_t* __restrict__ out) {
+  const int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (it >= n_items) return;
+  const int64_t b = item_begin[it];
+  const int len = item_len[it];
+  int n = 0;
+  for (int t = lane; t < len; t += 32) n += vals[b + t] > 0.f;
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0) out[it] = n;
+}
+
+int als_count_positive(const float* vals, const int64_t* item_begin, const int32_t* item_len, int64_t n_items, int32_t* out,
+                       cudaStream_t st) {
+  count_positive_kernel<<<(unsigned)((n_items * 32 + 255) / 256), 256, 0, st>>>(vals, item_begin, item_len, n_items, out);
+  HALS_LAUNCH_CHECK();
+  return 0;
+}
+
 // src != nullptr: fp32 source factors, split into `split_buf` first (the stateless C-ABI call).
 // src == nullptr: `split_buf` already holds the split source ([n_src + 1][128] bf16, row n_src all zero) -- the
 // engine keeps the factors in this form across half-steps: every solved row is written as fp32 (dst) AND as its
@@ -756,7 +800,7 @@ int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const flo
                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl, cudaStream_t st) {
   using namespace ws64;
   __nv_bfloat16* hl = reinterpret_cast<__nv_bfloat16*>(split_buf);
-  HALS_REQUIRE(n_src < (int64_t)1 << 24, "rank-64 kernel: at most 2^24 source rows");
+  HALS_REQUIRE(n_src < (int64_t)1 << 31, "at most 2^31 - 1 source rows");
   if (src != nullptr) {
     const int64_t nthreads = n_src * (K / 8);
     split_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(src, n_src, K, hl);

@@ -16,7 +16,11 @@ int als_half_step_tc128(const int32_t* colidx, const float* vals, const float* s
 int als_half_step_tc64(const int32_t* colidx, const float* vals, const float* src, int64_t n_src, float* dst,
                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, cudaStream_t st);
 int als_half_step_ws128(const int32_t* colidx, const uint32_t* vals_hl, const float* src, int64_t n_src, float* dst,
-                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl, cudaStream_t st);
+                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl,
+                        const float* gram, float* gram_tiles, cudaStream_t st);
+int als_pack_ratings_implicit(const float* vals, int64_t nnz, float alpha, uint32_t* out_hl, float* out_scale, cudaStream_t st);
+int als_count_positive(const float* vals, const int64_t* item_begin, const int32_t* item_len, int64_t n_items, int32_t* out,
+                       cudaStream_t st);
 int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const float* src, int64_t n_src, float* dst,
                        float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl, cudaStream_t st);
 int als_launch_split_bf16(const float* src, int64_t n_src, int k, void* out, cudaStream_t st);
@@ -40,15 +44,21 @@ static size_t slot_region_bytes(int64_t n_slots, int k) {
   const size_t KP = (size_t)padded_rank(k);
   return (size_t)(n_slots > 0 ? n_slots : 0) * (KP * KP + KP + 4) * sizeof(float);
 }
-// tensor-core path: explicit feedback, rank 64 (HALS_FORCE_SIMT=1 routes everything to the SIMT path)
-static bool use_tc(int k, int implicit) {
+// tensor-core path: explicit feedback at ranks 64 and 128; implicit feedback at rank 128 when the plan carries the
+// operands packed for this alpha (HALS_FORCE_SIMT=1 routes everything to the SIMT path)
+static bool use_tc(int k, int implicit, float alpha, const hals_als_plan* plan) {
   static const bool force_simt = [] { const char* e = getenv("HALS_FORCE_SIMT"); return e && e[0] == '1'; }();
-  return !force_simt && !implicit && (k == 64 || k == 128);
+  if (force_simt) return false;
+  if (!implicit) return (k == 64 || k == 128) && plan->packed_alpha == 0.f;
+  return k == 128 && plan->vals_hl && plan->vals_scale && plan->item_npos && plan->chunk_pos && plan->packed_alpha == alpha &&
+         alpha > 0.f;
 }
+constexpr size_t kGramTileBytes = 128 * 72 * sizeof(float);   // Y^T Y in the rank-128 solver's lane-tile order
 
 extern "C" size_t hals_als_workspace_bytes(int64_t n_slots, int k, int64_t n_src) {
   // [partial (A,b,n) slots][bf16 h|l split of the source factors, tensor-core path]
-  return slot_region_bytes(n_slots, k) + (size_t)(n_src > 0 ? n_src : 0) * 4 * (size_t)k + 1024;   // + one all-zero row
+  // [partial (A,b,n) slots][bf16 h|l split of the source factors + one all-zero row][Gram tiles (implicit, rank 128)]
+  return slot_region_bytes(n_slots, k) + (size_t)(n_src > 0 ? n_src : 0) * 4 * (size_t)k + 1024 + (k == 128 ? kGramTileBytes : 0);
 }
 
 // Work items: first every slice of every long row (big, uniform items first so that the
@@ -169,9 +179,10 @@ extern "C" int hals_als_half_step_split(const int32_t* colidx, int64_t m_dst, co
   HALS_REQUIRE(workspace != nullptr, "null workspace");
   if (workspace_bytes < slot_region_bytes(plan->n_slots, k) + 16) return fail(HALS_ERR_WORKSPACE, "%s: workspace too small%s", __func__);
   // rows without ratings are never written: the caller keeps them zero (fp32 and split)
+  HALS_REQUIRE(plan->packed_alpha == 0.f, "the plan's ratings are packed for implicit feedback");
   if (k == 128)
     return als_half_step_ws128(colidx, plan->vals_hl, nullptr, n_src, dst, reg, plan, (float*)workspace,
-                               const_cast<void*>(src_hl), dst_hl, (cudaStream_t)stream);
+                               const_cast<void*>(src_hl), dst_hl, nullptr, nullptr, (cudaStream_t)stream);
   return als_half_step_ws64(colidx, plan->vals_hl, nullptr, n_src, dst, reg, plan, (float*)workspace,
                             const_cast<void*>(src_hl), dst_hl, (cudaStream_t)stream);
 }
@@ -181,6 +192,23 @@ extern "C" int hals_als_pack_ratings(const float* vals, int64_t nnz, uint32_t* o
   if (nnz == 0) return 0;
   HALS_REQUIRE(vals && out, "null pointer");
   return als_pack_ratings(vals, nnz, out, (cudaStream_t)stream);
+}
+
+extern "C" int hals_als_pack_ratings_implicit(const float* vals, int64_t nnz, float alpha, uint32_t* out_hl, float* out_scale,
+                                              void* stream) {
+  HALS_REQUIRE(nnz >= 0, "negative count");
+  HALS_REQUIRE(alpha > 0.f, "alpha must be positive");
+  if (nnz == 0) return 0;
+  HALS_REQUIRE(vals && out_hl && out_scale, "null pointer");
+  return als_pack_ratings_implicit(vals, nnz, alpha, out_hl, out_scale, (cudaStream_t)stream);
+}
+
+extern "C" int hals_als_plan_count_positive(const float* vals, const int64_t* item_begin, const int32_t* item_len,
+                                            int64_t n_items, int32_t* item_npos, void* stream) {
+  HALS_REQUIRE(n_items >= 0, "negative count");
+  if (n_items == 0) return 0;
+  HALS_REQUIRE(vals && item_begin && item_len && item_npos, "null pointer");
+  return als_count_positive(vals, item_begin, item_len, n_items, item_npos, (cudaStream_t)stream);
 }
 
 extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, const float* vals,
@@ -205,14 +233,20 @@ extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, 
   if (workspace_bytes < hals_als_workspace_bytes(plan->n_slots, k, n_src))
     return fail(HALS_ERR_WORKSPACE, "%s: workspace too small%s", __func__);
   HALS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
-  if (use_tc(k, implicit)) {
+  if (use_tc(k, implicit, alpha, plan)) {
     void* split = reinterpret_cast<uint8_t*>(workspace) + slot_region_bytes(plan->n_slots, k);
+    if (implicit) {
+      float* tiles = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(split) + (size_t)n_src * 4 * (size_t)k + 1024);
+      return als_half_step_ws128(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split, nullptr, gram,
+                                 tiles, st);
+    }
     if (k == 128) {
       // HALS_TC128_IMPL=groups selects the round-1 kernel (two solver groups, no chunk table)
       static const bool old128 = [] { const char* e = getenv("HALS_TC128_IMPL"); return e && e[0] == 'g'; }();
       if (old128 || plan->vals_hl == nullptr || plan->chunk_pos == nullptr)
         return als_half_step_tc128(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
-      return als_half_step_ws128(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split, nullptr, st);
+      return als_half_step_ws128(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split, nullptr,
+                                 nullptr, nullptr, st);
     }
     // HALS_TC64_IMPL=cta4 selects the round-1 kernel (four 4-warp CTAs per SM); default: warp-specialised kernel
     static const bool old64 = [] { const char* e = getenv("HALS_TC64_IMPL"); return e && e[0] == 'c'; }();

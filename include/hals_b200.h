@@ -87,6 +87,13 @@ typedef struct hals_als_plan {
                                 hals_als_pack_ratings once per ratings matrix.  The rank-64 tensor-core kernel
                                 copies it straight into the MMA operand; NULL selects the slower kernel that
                                 converts the fp32 ratings itself. */
+  /* Implicit feedback on the tensor cores (rank 128; optional -- without them implicit mode runs the CUDA-core kernel).
+   * hals_als_pack_ratings_implicit fills vals_hl with (1 + c) / sqrt(c) where r > 0 (0 elsewhere) and vals_scale with
+   * sqrt(c), c = alpha |r|; hals_als_plan_count_positive fills item_npos.  packed_alpha records the alpha they were
+   * built for: 0 = vals_hl holds the plain ratings (explicit feedback). */
+  const float* vals_scale;   /* [nnz] sqrt(alpha |r|)                                      */
+  const int32_t* item_npos;  /* [n_items] ratings > 0 in the work item                     */
+  float packed_alpha;
 } hals_als_plan;
 
 /* Host-side planner (pure CPU, no CUDA): sizes first, then fill caller arrays.
@@ -110,6 +117,11 @@ size_t hals_als_workspace_bytes(int64_t n_slots, int k, int64_t n_src);
 int32_t hals_als_default_seg_len(int k);
 /* out[i] = bf16(vals[i]) | bf16(vals[i] - bf16(vals[i])) << 16 (device arrays); see hals_als_plan.vals_hl. */
 int hals_als_pack_ratings(const float* vals, int64_t nnz, uint32_t* out, void* stream);
+/* Implicit-feedback operands of the tensor-core kernel (see hals_als_plan.vals_scale); device arrays. */
+int hals_als_pack_ratings_implicit(const float* vals, int64_t nnz, float alpha, uint32_t* out_hl, float* out_scale,
+                                   void* stream);
+int hals_als_plan_count_positive(const float* vals, const int64_t* item_begin, const int32_t* item_len, int64_t n_items,
+                                 int32_t* item_npos, void* stream);
 
 int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, const float* vals,
                        int64_t m_dst, const float* src, int64_t n_src, float* dst, int k,

@@ -16,6 +16,10 @@ from tests.util import rel_l2
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 HS_REL, HS_ABS = 2e-5, 1e-4
+# Implicit feedback: the weights c = alpha |r| (up to several hundred) worsen the conditioning of the normal equations.
+# fp32 CUDA-core build: 5e-5.  Rank 128 on the tensor cores: the rows rescaled by sqrt(c) are re-split into bf16 hi/lo
+# (16-17 significant bits, twice the representation error of the explicit build): 2e-4.
+IMPL_TOL = {False: dict(rel=5e-5, ab=3e-4), True: dict(rel=2e-4, ab=1e-3)}
 
 
 def _mods():
@@ -30,7 +34,7 @@ def gpu_half_step(rows, cols, vals, n_rows, src, reg, implicit=False, alpha=1.0,
     shard = csr.build_csr(torch.as_tensor(rows).to(dev), torch.as_tensor(cols).to(dev),
                           torch.as_tensor(vals).to(dev), n_rows)
     k = src.shape[1]
-    plan = csr.AlsPlanHandle(shard, k, seg_len, n_src=src.shape[0])
+    plan = csr.AlsPlanHandle(shard, k, seg_len, n_src=src.shape[0], implicit=implicit, alpha=alpha)
     s = torch.from_numpy(np.ascontiguousarray(src)).to(dev)
     dst = torch.full((n_rows, k), 7.0, dtype=torch.float32, device=dev)   # poison: rows must be overwritten
     gram = None
@@ -86,7 +90,26 @@ def test_half_step_implicit_matches_oracle(k):
     got, _ = gpu_half_step(i, u, r, I, X, 0.05, implicit=True, alpha=40.0)
     rp, ci, v = als_oracle.coo_to_csr(i, u, r, I)
     want = c_oracle.als_half_step(rp, ci, v, X, 0.05, implicit=True, alpha=40.0)
-    assert_close(got, want, rel=5e-5, ab=3e-4)
+    assert_close(got, want, **IMPL_TOL[k == 128])
+
+
+@pytest.mark.parametrize("k", [64, 128])
+def test_implicit_long_rows_and_mixed_signs(k):
+    """Implicit feedback with sliced rows (rank 128: tensor-core build with rows rescaled by sqrt(c), Gram added in the
+    solver / the long-row reduce; rank 64: CUDA-core kernel), ratings of both signs, zeros and non-integer weights."""
+    U, I, nnz = 2500, 60, 24000
+    rng = np.random.default_rng(11)
+    p = 1.0 / np.arange(1, I + 1); p /= p.sum()
+    i, u = rng.choice(I, nnz, p=p), rng.integers(0, U, nnz)
+    r = (rng.gamma(1.5, 2.0, nnz) * rng.choice([1, 1, 1, -1, 0], nnz)).astype(np.float32)
+    X = als_oracle.init_factors(U, k, 4)
+    got, plan = gpu_half_step(i, u, r, I, X, 0.05, implicit=True, alpha=15.0, seg_len=96)
+    assert plan.n_long > 0
+    rp, ci, v = als_oracle.coo_to_csr(i, u, r, I)
+    want = c_oracle.als_half_step(rp, ci, v, X, 0.05, implicit=True, alpha=15.0)
+    assert_close(got, want, **IMPL_TOL[k == 128])
+    again, _ = gpu_half_step(i, u, r, I, X, 0.05, implicit=True, alpha=15.0, seg_len=96)
+    assert np.array_equal(got, again)
 
 
 @pytest.mark.parametrize("k,seg", [(10, 64), (64, 64), (128, 96), (64, 4096)])
