@@ -489,7 +489,8 @@ def main():
 
     u, i, r = synth_coo(w, dev)
     data_sum = coo_checksum(u, i, r)
-    eng = AlsEngine(u, i, r, w["users"], w["items"], w["rank"], w["reg"], device=dev, dist_rank=rank, world=world)
+    eng = AlsEngine(u, i, r, w["users"], w["items"], w["rank"], w["reg"], implicit=bool(w.get("implicit")),
+                    alpha=float(w.get("alpha", 1.0)), device=dev, dist_rank=rank, world=world)
     # every rank generated the SAME matrix and derived the SAME shard bounds (the all-gathers rely on it)
     assert_same_on_all_ranks([data_sum] + list(eng.user_bounds) + list(eng.item_bounds), "inputs / shard bounds", dev, world)
     eng.init_user_factors(1)
