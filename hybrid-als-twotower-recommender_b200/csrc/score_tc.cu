@@ -35,9 +35,22 @@ namespace hals {
 
 constexpr int kStM = 128;
 constexpr int kStRing = 4;
-constexpr int kStEpiWarps = 8;        // two epilogue warps per TMEM lane quarter, each takes half of the columns
+#ifndef HALS_SCORE_PARTS
+#define HALS_SCORE_PARTS 2
+#endif
+// Epilogue warps per TMEM lane quarter; each takes 1/kStParts of a tile's columns and feeds its own candidate stream.
+// 2 warps per scheduler leave the epilogue latency-bound (38 % of its samples are fixed-latency waits, ncu round 2), but
+// 4 (16 epilogue warps at 96 registers, twice the candidate streams) measured SLOWER on the 1M x 1.25M leg: extrema
+// pass 717 vs 632 ms, blend + top-k pass 879 vs 738 ms -- the extra streams cost more compactions and exact re-scoring
+// than the extra warps hide.
+constexpr int kStParts = HALS_SCORE_PARTS;
+static_assert(kStParts == 2 || kStParts == 4, "column parts per tile");
+constexpr int kStEpiWarps = 4 * kStParts;
 constexpr int kStThreads = 64 + 32 * kStEpiWarps;
 constexpr int kStExC = 4;            // extrema candidates per list
+#ifndef HALS_SCORE_W
+#define HALS_SCORE_W 64              // columns per filter step of pass 2 (a candidate buffer keeps W slots free; 32: 5 % slower)
+#endif
 
 struct ScoreTcArgs {
   int nkb_a, nkb_t;                  // 64-wide K blocks of the ALS / tower part
@@ -230,9 +243,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   } else {
     // ------------------------------------------------------------ epilogue: thread = user row
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;                   // which half of the tile's columns
-    const int vs = split * 2 + half;                    // candidate stream ("virtual split") of this thread
-    constexpr int HB = BN / 2;
+    const int half = (warp - 2) >> 2;                   // which part of the tile's columns
+    const int vs = split * kStParts + half;             // candidate stream ("virtual split") of this thread
+    constexpr int HB = BN / kStParts;
     const int r = q * 32 + lane;
     const int64_t u = u0 + r;
     const bool live = u < A.n_users;
@@ -274,14 +287,26 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
         // job m holds model m's scores (0 = ALS, 1 = tower): lists 2m (maxima) and 2m+1 (minima, as -s)
         const bool present = (m == 0) ? (A.nkb_a > 0) : (A.nkb_t > 0);
         if (present) {
-          float vv[2][32];
-          umma::tmem_ld32_issue(tbase + half * HB, vv[0]);
+          // The group loop is ROLLED (pairs of groups, for the register double buffer): fully unrolled, the epilogue was
+          // 60 KB of straight-line code that eight warps walk once per tile, and 37 % of the warp samples were
+          // instruction-fetch stalls (ncu, round 2).
+          // (four warps per scheduler: no register double buffer -- the other warps cover the tcgen05.ld latency and the
+          //  two candidate lists per model need the registers)
+          constexpr bool kDouble = kStParts < 4;
+          constexpr int NB = kDouble ? 2 : 1;
+          float vv[NB][32];
+          if (kDouble) umma::tmem_ld32_issue(tbase + half * HB, vv[0]);
+          static_assert(G % NB == 0, "groups are processed in pairs");
+#pragma unroll 1
+          for (int gp = 0; gp < G; gp += NB) {
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
+          for (int gb = 0; gb < NB; ++gb) {
+            const int g = gp + gb;
             const int c0 = half * HB + g * 32;
-            umma::tmem_wait_ld_dep(vv[g & 1]);
-            if (g + 1 < G) umma::tmem_ld32_issue(tbase + c0 + 32, vv[(g + 1) & 1]);
-            const float (&v)[32] = vv[g & 1];
+            if (!kDouble) umma::tmem_ld32_issue(tbase + c0, vv[0]);
+            umma::tmem_wait_ld_dep(vv[gb]);
+            if (kDouble && g + 1 < G) umma::tmem_ld32_issue(tbase + c0 + 32, vv[(gb + 1) % NB]);
+            const float (&v)[32] = vv[gb];
             // Extremes of each 8-column octet first (FMNMX3 chains).  A warp runs an octet's per-column code only
             // when some lane can change one of its two lists there, and that code walks 8 columns, not 32.
             const float t0 = xv[2 * m][kStExC - 1], t1 = xv[2 * m + 1][kStExC - 1];
@@ -315,25 +340,30 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
               }
             }
           }
+          }
         }
       } else {
         // W columns per step (two tcgen05.ld x32 in flight per buffer when the candidate buffer leaves room for 64
         // new keys): more independent FMNMX3 chains per wait, half as many waits, branches and ballots
-        constexpr int W = (CAP >= 256) ? 64 : 32;
+        constexpr int W = (CAP >= 256 && kStParts == 2) ? HALS_SCORE_W : 32;
         constexpr int G2 = HB / W;
+        static_assert(G2 % 2 == 0, "groups are processed in pairs");
         float vv[2][W];
 #pragma unroll
         for (int x = 0; x < W / 32; ++x) umma::tmem_ld32_issue(tbase + half * HB + 32 * x, vv[0] + 32 * x);
+#pragma unroll 1
+        for (int gp = 0; gp < G2; gp += 2) {
 #pragma unroll
-        for (int g = 0; g < G2; ++g) {
+        for (int gb = 0; gb < 2; ++gb) {
+          const int g = gp + gb;
           const int c0 = half * HB + g * W;
 #pragma unroll
-          for (int x = 0; x < W / 32; ++x) umma::tmem_wait_ld_dep(vv[g & 1] + 32 * x);
+          for (int x = 0; x < W / 32; ++x) umma::tmem_wait_ld_dep(vv[gb] + 32 * x);
           if (g + 1 < G2) {
 #pragma unroll
-            for (int x = 0; x < W / 32; ++x) umma::tmem_ld32_issue(tbase + c0 + W + 32 * x, vv[(g + 1) & 1] + 32 * x);
+            for (int x = 0; x < W / 32; ++x) umma::tmem_ld32_issue(tbase + c0 + W + 32 * x, vv[gb ^ 1] + 32 * x);
           }
-          const float (&v)[W] = vv[g & 1];
+          const float (&v)[W] = vv[gb];
           // Octet maxima (FMNMX3 chains) against the row threshold.  Survivors are ~0.4% of the items: most lanes
           // have none in a group, but some lane of the warp nearly always has one, so what matters is how much
           // code that lane drags the warp through -- an 8-column bitmask, and for the usual single survivor the
@@ -386,6 +416,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
             const int c_new = compact_row<CAP>(b, c_src, A.keep, lane, &t_new);
             if (lane == src) { cnt = c_new; thr = t_new; }
           }
+        }
         }
       }
       umma::fence_before_sync();
@@ -662,7 +693,7 @@ TcPlan make_plan(int64_t n_users, int64_t n_items, int ka, int kt, int topk) {
   p.splits = (int)((n_items + p.items_per_split - 1) / p.items_per_split);
   if (p.splits < 1) p.splits = 1;
   size_t o = 0;
-  const size_t su = 2 * (size_t)p.splits * (size_t)n_users;   // two candidate streams (column halves) per split
+  const size_t su = (size_t)kStParts * (size_t)p.splits * (size_t)n_users;   // kStParts candidate streams (column parts) per split
   {
     const int tk = topk > 0 ? topk : 1;
     const size_t plain = score_simt_workspace_bytes(n_users, n_items, tk);
@@ -748,7 +779,7 @@ extern "C" int hals_score_extrema(const float* Ua, int64_t ua_stride, const floa
   ScoreTcArgs A{p.nkb_a, p.nkb_t, n_users, n_items, p.items_per_split, p.splits, p.keep, 0};
   if (int rc = launch_tc<1, kTcBN, 128>(mu, mi, A, p.nkb_a + p.nkb_t, (float*)(W + p.off_exv), (int32_t*)(W + p.off_exi),
                                       nullptr, nullptr, nullptr, st)) return rc;
-  ExactArgs E{Ua, ua_stride, Ia, ia_stride, ka, Ut, ut_stride, It, it_stride, kt, n_users, 2 * p.splits};
+  ExactArgs E{Ua, ua_stride, Ia, ia_stride, ka, Ut, ut_stride, It, it_stride, kt, n_users, kStParts * p.splits};
   score_exact_extrema_kernel<<<(unsigned)((n_users * 4 + 7) / 8), 256, 0, st>>>(
       E, (const float*)(W + p.off_exv), (const int32_t*)(W + p.off_exi), unorm, inorm, extrema, flag);
   HALS_LAUNCH_CHECK();
@@ -803,7 +834,7 @@ extern "C" int hals_score_blend_topk(const float* Ua, int64_t ua_stride, const f
   else if (p.cap == 256) rc = launch_tc<2, kTcBN, 256>(mu, mi, A, p.nkb_a + p.nkb_t, nullptr, nullptr, cand, cnt, thr, st);
   else rc = launch_tc<2, kTcBN, 512>(mu, mi, A, p.nkb_a + p.nkb_t, nullptr, nullptr, cand, cnt, thr, st);
   if (rc) return rc;
-  const int vsplits = 2 * p.splits;
+  const int vsplits = kStParts * p.splits;
   ExactArgs E{Ua, ua_stride, Ia, ia_stride, ka, Ut, ut_stride, It, it_stride, kt, n_users, vsplits};
   int sortn = 64;
   while (sortn < p.keep) sortn <<= 1;                   // streams leave the tensor-core kernel trimmed to `keep` keys
