@@ -180,13 +180,19 @@ class TwoTowerModel:
         import torch
         import torch.nn.functional as F
         E = self.embedding_size
-        u = F.layer_norm(p["user_emb"][torch.as_tensor(f["user_in"], device=dev).long()], (E,),
-                         p["user_ln_g"], p["user_ln_b"], LN_EPS)
+
+        def rows(table, ids):
+            # an id outside its table reads as a zero embedding row: what the tower kernels (csrc/towers.cu) and a Keras
+            # Embedding on the GPU do -- validation users never seen in training land here
+            ids = torch.as_tensor(np.asarray(ids), device=dev).long()
+            ok = (ids >= 0) & (ids < table.shape[0])
+            return table[torch.where(ok, ids, torch.zeros_like(ids))] * ok.unsqueeze(1).to(table.dtype)
+
+        u = F.layer_norm(rows(p["user_emb"], f["user_in"]), (E,), p["user_ln_g"], p["user_ln_b"], LN_EPS)
         num = torch.as_tensor(np.asarray(f["numeric_in"], dtype=np.float32), device=dev)
         h = torch.relu(num @ p["num_w"] + p["num_b"])
-        cat = torch.cat([p["item_emb"][torch.as_tensor(f["item_id_in"], device=dev).long()],
-                         p["manu_emb"][torch.as_tensor(f["manufacturer_in"], device=dev).long()],
-                         p["cat_emb"][torch.as_tensor(f["category_in"], device=dev).long()], h], dim=1)
+        cat = torch.cat([rows(p["item_emb"], f["item_id_in"]), rows(p["manu_emb"], f["manufacturer_in"]),
+                         rows(p["cat_emb"], f["category_in"]), h], dim=1)
         i = F.layer_norm(cat @ p["out_w"] + p["out_b"], (E,), p["item_ln_g"], p["item_ln_b"], LN_EPS)
         return (u * i).sum(dim=1)
 
@@ -199,9 +205,19 @@ class TwoTowerModel:
         dev = self.model.t["user_emb"].device
         params = {k: v.clone().requires_grad_(True) for k, v in self.model.t.items()}
         opt = torch.optim.Adam(list(params.values()), lr=self.learning_rate, eps=1e-7)
+        has_val = val_data is not None and len(val_data) > 0
+        # Embedding ids are table rows (two_tower_model.py:47-62).  Keras on the CPU raises InvalidArgumentError for a
+        # TRAINING id outside its table: checked here on the host.  (Validation rows may name users / items the tables
+        # do not have -- the reference's own hyperparameter_tuning holds out whole users -- they read as zero rows.)
+        for frame in (train_data,):
+            for col, table in (("userId", "user_emb"), ("itemId", "item_emb"), ("manufacturer_id", "manu_emb"),
+                               ("category_id", "cat_emb")):
+                ids = frame[col].values
+                n_rows = int(self.model.t[table].shape[0])
+                if len(ids) and (ids.min() < 0 or ids.max() >= n_rows):
+                    raise IndexError(f"{col}: ids must lie in [0, {n_rows}) (found {int(ids.min())}..{int(ids.max())})")
         tf = self._prepare_features(train_data)
         y = torch.as_tensor(train_data["average_review_rating"].values.astype(np.float32), device=dev)
-        has_val = val_data is not None and len(val_data) > 0
         vf = self._prepare_features(val_data) if has_val else None
         vy = torch.as_tensor(val_data["average_review_rating"].values.astype(np.float32), device=dev) if has_val else None
         if has_val:  # _prepare_features re-fits the scaler (reference behaviour); keep the train fit for predict
@@ -220,7 +236,7 @@ class TwoTowerModel:
                 opt.zero_grad(set_to_none=True)
                 loss.backward()
                 opt.step()
-                tot += float(loss) * len(b)
+                tot += float(loss.detach()) * len(b)
             history["loss"].append(tot / max(n, 1))
             if has_val:
                 with torch.no_grad():
@@ -263,6 +279,51 @@ class TwoTowerModel:
         loaded_model.scaler = scaler
         loaded_model.is_trained = True
         return loaded_model
+
+
+def hyperparameter_tuning(train_data, param_grid, val_size=0.2, random_state=42):
+    """F1@10-based grid search over {batch_size, epochs} (src/two_tower_model.py:169-236): hold out `val_size` of the
+    users, train one TwoTowerModel(embedding_size=50, learning_rate=0.001) per grid entry on the rest, score the first 50
+    held-out users against the held-out items with predict_for_user (the GPU tower kernels) and keep the entry with the
+    best mean F1@10.  Returns the best entry (a copy) or None; an entry that raises is reported and skipped, like the
+    reference.  One deviation: the reference passes `random_state` to np.random.choice, which has no such argument (its
+    call raises TypeError before anything runs); the held-out users are drawn from np.random.RandomState(random_state)."""
+    best_params = None
+    best_f1 = 0.0
+    train_users = train_data['userId'].unique()
+    rng = np.random.RandomState(random_state)
+    val_users = rng.choice(train_users, size=int(len(train_users) * val_size), replace=False)
+    train_sub = train_data[~train_data['userId'].isin(val_users)]
+    val_sub = train_data[train_data['userId'].isin(val_users)]
+    num_users = train_sub['userId'].nunique()
+    num_items = train_sub['itemId'].nunique()
+    num_manufacturers = train_sub['manufacturer_id'].nunique()
+    num_categories = train_sub['category_id'].nunique()
+    for params in param_grid:
+        print(f"\nTesting parameters: {params}")
+        try:
+            model = TwoTowerModel(num_users=num_users, num_items=num_items, num_manufacturers=num_manufacturers,
+                                  num_categories=num_categories, embedding_size=50, learning_rate=0.001)
+            model.train(train_sub, val_sub, batch_size=params['batch_size'], epochs=params['epochs'])
+            f1_scores = []
+            sample_users = val_sub['userId'].unique()[:50]
+            items = val_sub[['itemId', 'manufacturer_id', 'category_id', 'price',
+                             'average_review_rating']].drop_duplicates()
+            for user_id in sample_users:
+                rows = val_sub[val_sub['userId'] == user_id]
+                actual = dict(zip(rows['itemId'], rows['average_review_rating']))
+                preds = model.predict_for_user(user_id, items)
+                f1_scores.append(compute_f1_score(actual, dict(preds), k=10))
+            avg_f1 = np.mean(f1_scores)
+            print(f"  Avg F1@10: {avg_f1:.4f}")
+            if avg_f1 > best_f1:
+                best_f1 = avg_f1
+                best_params = params.copy()
+                print(f"  New best F1@10: {best_f1:.4f}")
+        except Exception as e:
+            print(f"  Error with params {params}: {str(e)}")
+            continue
+    return best_params
 
 
 def compute_f1_score(actual, pred, k=10):

@@ -385,3 +385,38 @@ def test_train_compacts_raw_ids_on_the_device(tmp_path):
     assert np.abs(als.model.item_factors.cpu().numpy() - Yo).max() <= 1e-3
     assert als.global_mean == pytest.approx(float(r.mean()), abs=1e-6)
     assert set(als.item_features.keys()) == set(iid.tolist())             # built lazily from the training frame
+
+
+@pytest.mark.gpu
+def test_hyperparameter_tuning_grid_search():
+    """two_tower_model.hyperparameter_tuning (src/two_tower_model.py:169-236): returns one of the grid entries (a copy),
+    trains on the users that are not held out and scores the held-out users through predict_for_user."""
+    import pandas as pd
+    from hybrid_als_twotower_recommender_b200 import two_tower_model as ttm
+    rng = np.random.default_rng(5)
+    U, I, nnz = 40, 30, 900
+    u, i = rng.integers(0, U, nnz), rng.integers(0, I, nnz)
+    # the function sizes the embedding tables by nunique() of the TRAINING part, so ids must be compact there: give the
+    # users it will hold out (same draw as the function) the highest ids
+    seen = pd.unique(u)                                  # order of first appearance, what the function draws from
+    held = np.random.RandomState(7).choice(seen, size=int(len(seen) * 0.25), replace=False)
+    order = np.concatenate([np.setdiff1d(np.arange(U), held), held])
+    relabel = np.empty(U, np.int64); relabel[order] = np.arange(len(order))
+    u = relabel[u]
+    manu_of, cat_of, price_of = rng.integers(0, 4, I), rng.integers(0, 3, I), rng.uniform(5, 50, I)
+    rating_of = rng.integers(1, 6, I).astype(float)     # ratings follow the item: some grid entry reaches F1@10 > 0
+    df = pd.DataFrame({"userId": u, "itemId": i, "average_review_rating": rating_of[i],
+                       "manufacturer_id": manu_of[i], "category_id": cat_of[i], "price": price_of[i]})
+    grid = [{"batch_size": 64, "epochs": 1}, {"batch_size": 128, "epochs": 2}]
+    import contextlib, io
+    log = io.StringIO()
+    with contextlib.redirect_stdout(log):
+        best = ttm.hyperparameter_tuning(df, grid, val_size=0.25, random_state=7)
+    assert "Error with params" not in log.getvalue(), log.getvalue()
+    assert best in grid and all(best is not g for g in grid)
+    # an entry that raises (missing key; ids outside the tables) is reported and skipped, like the reference
+    assert ttm.hyperparameter_tuning(df, [{"batch_size": 64}], val_size=0.25, random_state=7) is None
+    bad = df.copy(); bad["userId"] = bad["userId"] + 1000
+    with contextlib.redirect_stdout(log):
+        assert ttm.hyperparameter_tuning(bad, grid, val_size=0.25, random_state=7) is None
+    assert "ids must lie in" in log.getvalue()
