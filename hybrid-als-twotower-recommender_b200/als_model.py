@@ -256,6 +256,11 @@ class ALSModel:
             import torch
             if not self.initialize_spark():
                 return None
+            if os.path.isdir(model_path) and not os.path.exists(f"{model_path}.npz"):
+                # what the reference's ALSModel.save_model writes (als_model.py:116-127): a Spark ALSModel directory
+                raise ValueError(f"{model_path} is a Spark ALSModel directory (parquet userFactors/itemFactors); this "
+                                 "package stores factors as <path>.npz -- export them with numpy (ids, features) and "
+                                 "save through ALSModel.save_model, see INTEGRATION.md")
             z = np.load(f"{model_path}.npz")
             dev = torch.device("cuda")
             self.model = ALSFactors(int(z["rank"]), z["user_ids"], z["item_ids"],

@@ -268,7 +268,16 @@ class TwoTowerModel:
         from . import _native as nat
         nat.lib()
         nat.require_cuda()
-        z = np.load(model_path)
+        try:
+            z = np.load(model_path)
+            missing = [k for k in TowerParams.NAMES if k not in z.files]
+        except Exception as e:       # a Keras v3 archive (what the reference's save_model writes) is a zip of config + h5
+            raise ValueError(f"{model_path} is not a tower checkpoint of this package (numpy .npz written by "
+                             f"TwoTowerModel.save_model); a Keras archive has to be exported layer by layer, see "
+                             f"INTEGRATION.md ({e})") from e
+        if missing:
+            raise ValueError(f"{model_path}: not a tower checkpoint of this package (missing arrays {missing[:3]}...); "
+                             "Keras archives have to be exported layer by layer, see INTEGRATION.md")
         with open(f"{model_path}_scaler.pkl", "rb") as f:
             scaler = pickle.load(f)
         params = TowerParams.from_numpy({k: z[k] for k in TowerParams.NAMES}, torch.device("cuda"))
