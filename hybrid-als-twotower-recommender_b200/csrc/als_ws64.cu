@@ -342,13 +342,19 @@ __device__ __noinline__ void drain_role(uint32_t slots, uint32_t tmem, Bars* bar
 template <int JR>
 __device__ __forceinline__ void elim_block(f32x2 (&R)[36], f32x2& bb2, const uint32_t P, const uint32_t Y,
                                            const uint32_t DI, const int ti, const int tj, const int lane) {
-  const uint32_t oW = (uint32_t)ti * 64u;                                  // P[ti][q]: my rows' entries
-  const uint32_t oL = (uint32_t)(tj & 3) * 64u + (uint32_t)(tj >> 2) * 4u; // entry of row n = tj + 8c: P[tj&3][c][tj>>2]
-  const uint32_t oB = oW + (uint32_t)tj * 8u;                              // my right-hand-side rows: P[ti][tj]
-  {   // column 8*JR goes out first (owners: tj == 0), into buffer 0; lane 0 holds its diagonal and publishes -1/d
-    const bool own = (tj == 0);
+  // Published column: P[q / 2][ti][q % 2][half] (row ti + 4 half + 8 q).  The first layout, P[ti][q][half], put rows
+  // ti and ti + 2 on the same banks: every column-value load and every publish was a 2-way conflict, and the solver
+  // warps keep the SM's one shared-memory pipe 72 % busy (ncu, user half of c2) -- wavefronts are what this loop pays.
+  const uint32_t oW = (uint32_t)ti * 16u;                                  // my rows: + (q / 2) * 64 + (q % 2) * 8
+  const uint32_t oL = (uint32_t)(tj & 3) * 16u + (uint32_t)(tj >> 2) * 4u; // row n = tj + 8c: + (c / 2) * 64 + (c % 2) * 8
+  const uint32_t oB = oW + (uint32_t)(tj >> 1) * 64u + (uint32_t)(tj & 1) * 8u;   // my right-hand-side rows (q = tj)
+  auto publish = [&](uint32_t Pn, bool own) {
+    if (JR & 1) sts64_if(own, Pn + oW + (JR >> 1) * 64 + 8, R[tri(JR, JR)]);
 #pragma unroll
-    for (int q = JR; q < 8; ++q) sts64_if(own, P + oW + q * 8, R[tri(q, JR)]);
+    for (int q = (JR + 1) & ~1; q < 8; q += 2) sts128x2_if(own, Pn + oW + (q >> 1) * 64, R[tri(q, JR)], R[tri(q + 1, JR)]);
+  };
+  {   // column 8*JR goes out first (owners: tj == 0), into buffer 0; lane 0 holds its diagonal and publishes -1/d
+    publish(P, tj == 0);
     sts32_if(ti == 0 && tj == JR, Y + (uint32_t)(8 * JR) * 4u, lo2(bb2));
     sts32_if(lane == 0, DI + (uint32_t)(8 * JR) * 4u, -rcp_fast(lo2(R[tri(JR, JR)])));
     __syncwarp();
@@ -360,12 +366,12 @@ __device__ __forceinline__ void elim_block(f32x2 (&R)[36], f32x2& bb2, const uin
     const uint32_t Pj = P + ((uint32_t)(jm & 1) << 8);
     f32x2 w[8];
     float l[8];
-    if (JR & 1) w[JR] = lds64x2(Pj + oW + JR * 8);
+    if (JR & 1) w[JR] = lds64x2(Pj + oW + (JR >> 1) * 64 + 8);
 #pragma unroll
-    for (int q = (JR + 1) & ~1; q < 8; q += 2) lds128x2(Pj + oW + q * 8, w[q], w[q + 1]);
+    for (int q = (JR + 1) & ~1; q < 8; q += 2) lds128x2(Pj + oW + (q >> 1) * 64, w[q], w[q + 1]);
     const float ninv = lds32(DI + (uint32_t)j * 4u);
 #pragma unroll
-    for (int c = JR; c < 8; ++c) l[c] = lds32(Pj + oL + c * 8);
+    for (int c = JR; c < 8; ++c) l[c] = lds32(Pj + oL + (c >> 1) * 64 + (c & 1) * 8);
     const float zj = lds32(Y + (uint32_t)j * 4u);
     const f32x2 wb = lds64x2(Pj + oB);
     const f32x2 ninv2 = pack2(ninv, ninv);
@@ -395,8 +401,7 @@ __device__ __forceinline__ void elim_block(f32x2 (&R)[36], f32x2& bb2, const uin
     {   // publish column j + 1 (jm == 7: nobody owns "column 8" of the block -- no store, no branch either)
       const uint32_t Pn = P + ((uint32_t)(jn & 1) << 8);
       const bool own = (tj == jn);
-#pragma unroll
-      for (int q = JR; q < 8; ++q) sts64_if(own, Pn + oW + q * 8, R[tri(q, JR)]);
+      publish(Pn, own);
       sts32_if(tj == JR && ti == (jn & 3) && jn < 8, Y + (uint32_t)(j + 1) * 4u, (jn & 4) ? hi2(bb2) : lo2(bb2));
       sts32_if(own && ti == (jn & 3), DI + (uint32_t)(j + 1) * 4u, ninv_n);
       __syncwarp();

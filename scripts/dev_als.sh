@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 tag=$1; shift || true
 python -c "import __graft_entry__ as g; g.build()" 2>&1 | grep -v "nvcc warning" || true
 scripts/build_prof.sh 2>&1 | grep -v "nvcc warning" || true
-gpurun --timeout 900 -- "mkdir -p gpurun_out/$tag; timeout -k 5 150 python -m pytest tests/test_gpu_als.py -x -q -m gpu > gpurun_out/$tag/t_als.log 2>&1; echo \"tests rc=\$?\" >> gpurun_out/$tag/t_als.log; timeout -k 5 120 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-scoring --no-c3 $* > gpurun_out/$tag/b_ws.log 2>&1; HALS_LIB_PATH=\$PWD/hybrid-als-twotower-recommender_b200/libhals_b200_prof.so timeout -k 5 120 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-scoring --no-c3 --no-graphs $* > gpurun_out/$tag/b_prof.log 2>&1; tail -3 gpurun_out/$tag/t_als.log" 2>&1 | tail -5
+gpurun --timeout 900 -- "mkdir -p gpurun_out/$tag; timeout -k 5 150 python -m pytest tests/test_gpu_als.py -x -q -m gpu > gpurun_out/$tag/t_als.log 2>&1; echo \"tests rc=\$?\" >> gpurun_out/$tag/t_als.log; timeout -k 5 120 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-scoring --no-c3 --no-c4 $* > gpurun_out/$tag/b_ws.log 2>&1; HALS_LIB_PATH=\$PWD/hybrid-als-twotower-recommender_b200/libhals_b200_prof.so timeout -k 5 120 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-scoring --no-c3 --no-graphs $* > gpurun_out/$tag/b_prof.log 2>&1; tail -3 gpurun_out/$tag/t_als.log" 2>&1 | tail -5
 python3 - <<PY
 import json,re,collections
 d=json.loads(open('gpurun_out/$tag/b_ws.log').read().strip().splitlines()[-1])
