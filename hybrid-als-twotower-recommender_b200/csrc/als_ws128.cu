@@ -39,7 +39,7 @@ constexpr int KC = 32;
 constexpr int kRowBytes = 128;               // one 64-wide bf16 MN atom row
 constexpr int kBlk = KC * kRowBytes;         // 4096: one [KC][64] block
 constexpr int kStageBytes = 5 * kBlk;        // H0 | H1 | L0 | L1 | R
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 constexpr int kLdc = 132;                    // hand-over row stride (floats)
 constexpr int kCBytes = 128 * kLdc * 4 + 512;            // C | b
 constexpr int kGroups = 3;
