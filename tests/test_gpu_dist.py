@@ -36,9 +36,16 @@ def _worker(rank, world, port, case, out_dir):
     from hybrid_als_twotower_recommender_b200 import als_engine, scoring
     z = np.load(case)
     U, I, k = int(z["U"]), int(z["I"]), int(z["k"])
-    eng = als_engine.AlsEngine(z["u"], z["i"], z["r"], U, I, k, 0.1, device=dev, dist_rank=rank, world=world,
-                               seg_len=int(z["seg"]))
+    implicit = bool(z["implicit"]) if "implicit" in z.files else False
+    eng = als_engine.AlsEngine(z["u"], z["i"], z["r"], U, I, k, 0.1, implicit=implicit, alpha=float(z["alpha"]) if implicit else 1.0,
+                               device=dev, dist_rank=rank, world=world, seg_len=int(z["seg"]))
     eng.set_user_factors(z["X0"])
+    if implicit:      # fit only: the implicit engine has no RMSE of its own, scoring is covered by the explicit cases
+        X, Y = eng.fit(2)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), X=X.cpu().numpy(), Y=Y.cpu().numpy())
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if bool(z["graphs"]):
         assert eng.enable_graphs(), "graph capture of a half-step incl. its NCCL all-gather"
     X, Y = eng.fit(3)
@@ -112,3 +119,30 @@ def test_two_gpu_fit_and_scoring_match_one_gpu_and_oracle(tmp_path, k, graphs):
     assert np.abs(got_s[diff] - s1[diff]).max(initial=0.0) <= 2e-6
     wi, ws = hybrid_oracle.hybrid_topk_dense(Ua, Ia, Ut, It, 0.8, 0.2, topk)
     assert np.allclose(got_s, ws, atol=1e-5) and (got_i == wi).mean() > 0.995
+
+
+def test_two_gpu_implicit_rank128_matches_one_gpu_and_oracle(tmp_path):
+    """Config 4's path at N > 1: Hu-Koren half-steps on the tensor cores (rank 128), tensor-core Gram on every rank,
+    fp32 factor all-gather.  Two sweeps vs the single-GPU engine and vs the fp64 oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one box (gpurun --gpus 2)")
+    import hybrid_als_twotower_recommender_b200  # noqa: F401
+    from hybrid_als_twotower_recommender_b200 import als_engine
+    rng = np.random.default_rng(77)
+    U, I, nnz, k, alpha = 4000, 2500, 120_000, 128, 10.0
+    p = 1.0 / np.arange(1, I + 1); p /= p.sum()
+    u, i = rng.integers(0, U, nnz), rng.choice(I, nnz, p=p)
+    r = (rng.geometric(0.4, nnz) * rng.choice([1, 1, 1, -1, 0], nnz)).astype(np.float32)
+    X0 = als_oracle.init_factors(U, k, 5)
+    case = str(tmp_path / "case.npz")
+    np.savez(case, u=u, i=i, r=r, U=U, I=I, k=k, X0=X0, seg=1024, graphs=False, implicit=True, alpha=alpha)
+    mp.spawn(_worker, args=(2, _free_port(), case, str(tmp_path)), nprocs=2, join=True)
+    outs = [np.load(tmp_path / f"rank{q}.npz") for q in range(2)]
+    assert np.array_equal(outs[0]["X"], outs[1]["X"]) and np.array_equal(outs[0]["Y"], outs[1]["Y"])
+    eng = als_engine.AlsEngine(u, i, r, U, I, k, 0.1, implicit=True, alpha=alpha, seg_len=1024)
+    eng.set_user_factors(X0)
+    X1, Y1 = eng.fit(2)
+    assert rel_l2(outs[0]["X"], X1.cpu().numpy()) <= 2e-5 and rel_l2(outs[0]["Y"], Y1.cpu().numpy()) <= 2e-5
+    Xo, Yo = als_oracle.als_fit(u, i, r, U, I, k, 2, 0.1, X0, implicit=True, alpha=alpha,
+                                half_step=c_oracle.als_half_step)
+    assert rel_l2(outs[0]["X"], Xo) <= 1e-3 and rel_l2(outs[0]["Y"], Yo) <= 1e-3
