@@ -138,10 +138,18 @@ class AlsPlanHandle:
                 h[name][: self.n_long] = h[name][: self.n_long][order]
             n_gt16 = int((h["long_nseg"][: self.n_long] > 16).sum())
             n_gt256 = int((h["long_nseg"][: self.n_long] > 256).sum())
-        # chunk table (pieces of 32 ratings) + cost prefix: what the persistent rank-64 / rank-128 kernels stream
+        # chunk table (pieces of 32 ratings) + cost prefix: what the persistent rank-64 / rank-128 kernels stream.
+        # On a CUDA device the table is derived there from the item arrays (a few torch ops on ~1 M entries); the host
+        # planner entry point hals_als_plan_chunks_host computes the same thing for C callers and CPU tests
+        # (tests/test_gpu_als.py checks the two against each other).  Building it on the host and uploading ~20 MB of
+        # pageable memory was a third of the engine's set-up time on the MovieLens-20M shape.
         self.n_chunks = 0
-        if k in (64, 128) and self.n_items > 0:
-            self.n_chunks = int(L.hals_als_plan_chunk_count_host(nat.ptr(h["item_len"]), self.n_items))
+        dev = device if device is not None else shard.colidx.device
+        on_cuda = torch.device(dev).type == "cuda"
+        want_chunks = k in (64, 128) and self.n_items > 0
+        if want_chunks:
+            self.n_chunks = int(((h["item_len"][: self.n_items].astype(np.int64) + 31) // 32).sum())
+        if want_chunks and not on_cuda:
             h["item_chunk0"] = np.empty(self.n_items + 1, np.int64)
             h["item_cost0"] = np.empty(self.n_items + 1, np.int64)
             h["chunk_pos"] = np.empty(max(self.n_chunks, 1), np.int64)
@@ -150,8 +158,21 @@ class AlsPlanHandle:
                                                   self.n_items, int(k), nat.ptr(h["item_chunk0"]), nat.ptr(h["item_cost0"]),
                                                   nat.ptr(h["chunk_pos"]), nat.ptr(h["chunk_cnt"])), "plan_chunks")
         self.host = h
-        dev = device if device is not None else shard.colidx.device
         self.dev = {n: torch.from_numpy(a).to(dev) for n, a in h.items()}
+        if want_chunks and on_cuda:
+            n = self.n_items
+            il, ib, isl = self.dev["item_len"][:n].long(), self.dev["item_begin"][:n], self.dev["item_slot"][:n]
+            nch = (il + 31) // 32
+            solve, park = (32, 6) if k > 64 else (6, 2)                 # == kSolveCost / kParkCost of csrc/api.cu
+            c0 = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(nch, 0, out=c0[1:])
+            cost0 = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(nch + torch.where(isl < 0, solve, park), 0, out=cost0[1:])
+            item_of = torch.repeat_interleave(torch.arange(n, device=dev), nch, output_size=self.n_chunks)
+            k_in = torch.arange(self.n_chunks, device=dev) - c0[item_of]
+            self.dev["item_chunk0"], self.dev["item_cost0"] = c0, cost0
+            self.dev["chunk_pos"] = ib[item_of] + 32 * k_in
+            self.dev["chunk_cnt"] = (il[item_of] - 32 * k_in).to(torch.int32)
         # ratings as bf16 hi|lo pairs, packed once: the tensor-core kernels copy them into its operand
         # (implicit feedback, rank 128: the Hu-Koren operands -- see hals_als_plan.vals_scale in include/hals_b200.h)
         self.vals_hl = self.vals_scale = self.item_npos = None
@@ -179,6 +200,6 @@ class AlsPlanHandle:
             vals_scale=self.vals_scale.data_ptr() if self.vals_scale is not None else None,
             item_npos=self.item_npos.data_ptr() if self.item_npos is not None else None, packed_alpha=self.packed_alpha,
             n_long_gt16=n_gt16 if self.n_long else 0, n_long_gt256=n_gt256 if self.n_long else 0,
-            **{n: self.dev[n].data_ptr() for n in h})
+            **{n: t.data_ptr() for n, t in self.dev.items()})
         self.workspace_bytes = int(L.hals_als_workspace_bytes(self.n_slots, k, int(n_src)))
         self.workspace = torch.empty(max(self.workspace_bytes, 16), dtype=torch.uint8, device=dev)

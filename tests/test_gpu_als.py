@@ -283,3 +283,31 @@ def test_gram_and_predict():
     want = als_oracle.als_predict(X, Y, uu, ii, user_present=up.astype(bool))
     assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(got).sum() > 0
     assert np.allclose(got[~np.isnan(got)], want[~np.isnan(want)], atol=2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [64, 128])
+def test_device_chunk_table_equals_the_host_planner(k):
+    """AlsPlanHandle derives the chunk table on the device; hals_als_plan_chunks_host (the C-ABI planner a C caller
+    uses) must give exactly the same arrays."""
+    als_engine, csr = _mods()
+    nat = _nat()
+    rng = np.random.default_rng(9)
+    counts = rng.integers(0, 300, 4000); counts[[7, 900]] = [9000, 70000]
+    rows = np.repeat(np.arange(len(counts)), counts)
+    cols = rng.integers(0, 500, rows.size)
+    vals = rng.integers(1, 6, rows.size).astype(np.float32)
+    dev = torch.device("cuda")
+    shard = csr.build_csr(torch.as_tensor(rows).to(dev), torch.as_tensor(cols).to(dev), torch.as_tensor(vals).to(dev), len(counts))
+    plan = csr.AlsPlanHandle(shard, k, 1024, n_src=500)
+    n, h = plan.n_items, plan.host
+    L = nat.lib()
+    nch = int(L.hals_als_plan_chunk_count_host(nat.ptr(h["item_len"]), n))
+    assert nch == plan.n_chunks
+    c0, cost0 = np.empty(n + 1, np.int64), np.empty(n + 1, np.int64)
+    pos, cnt = np.empty(nch, np.int64), np.empty(nch, np.int32)
+    nat.check(L.hals_als_plan_chunks_host(nat.ptr(h["item_len"]), nat.ptr(h["item_begin"]), nat.ptr(h["item_slot"]), n, k,
+                                          nat.ptr(c0), nat.ptr(cost0), nat.ptr(pos), nat.ptr(cnt)))
+    for name, want in (("item_chunk0", c0), ("item_cost0", cost0), ("chunk_pos", pos), ("chunk_cnt", cnt)):
+        got = plan.dev[name].cpu().numpy()
+        assert got.dtype == want.dtype and np.array_equal(got, want), name
