@@ -249,11 +249,13 @@ class AlsEngine:
             self._fp32_stale = False
 
     def init_user_factors(self, seed: int = 0):
-        """Spark's `initialize` distribution: N(0,1) rows scaled to unit L2 norm."""
-        g = torch.Generator(device="cpu").manual_seed(int(seed))
-        f = torch.randn((self.n_users, self.k), generator=g, dtype=torch.float32)
+        """Spark's `initialize` distribution: N(0,1) rows scaled to unit L2 norm.  Drawn on the device the engine runs on
+        (CUDA: Philox, the same values on every rank and run for a given seed; drawing 9 M normals on the host and
+        uploading them cost more than a whole sweep on the MovieLens-20M shape)."""
+        g = torch.Generator(device=self.device).manual_seed(int(seed))
+        f = torch.randn((self.n_users, self.k), generator=g, dtype=torch.float32, device=self.device)
         f = f / f.norm(dim=1, keepdim=True).clamp_min(1e-30)
-        self.X.copy_(f.to(self.device))
+        self.X.copy_(f)
         self._after_user_init()
 
     def _gram_of(self, src):
