@@ -174,11 +174,11 @@ class AlsPlanHandle:
             self.dev["chunk_pos"] = ib[item_of] + 32 * k_in
             self.dev["chunk_cnt"] = (il[item_of] - 32 * k_in).to(torch.int32)
         # ratings as bf16 hi|lo pairs, packed once: the tensor-core kernels copy them into its operand
-        # (implicit feedback, rank 128: the Hu-Koren operands -- see hals_als_plan.vals_scale in include/hals_b200.h)
+        # (implicit feedback, ranks 64 / 128: the Hu-Koren operands -- see hals_als_plan.vals_scale in include/hals_b200.h)
         self.vals_hl = self.vals_scale = self.item_npos = None
         self.packed_alpha = 0.0
         on_gpu = torch.device(dev).type == "cuda" and shard.vals.numel() > 0
-        if implicit and k == 128 and on_gpu and alpha > 0 and self.n_items > 0:
+        if implicit and k in (64, 128) and on_gpu and alpha > 0 and self.n_items > 0:
             nnz = shard.vals.numel()
             self.vals_hl = torch.empty(nnz, dtype=torch.int32, device=dev)
             self.vals_scale = torch.empty(nnz, dtype=torch.float32, device=dev)

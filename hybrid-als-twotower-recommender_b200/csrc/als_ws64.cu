@@ -56,6 +56,7 @@ static_assert(kWarpSolver + kSolvers == kWarpGather && kWarpDrain + 4 == kThread
 
 struct Bars {
   uint64_t st_full[kStages], st_free[kStages];
+  uint64_t st_scaled[kStages];   // implicit mode: stage rescaled by sqrt(c) (what the MMA warp then waits for)
   uint64_t acc_full[kAcc], acc_free[kAcc];
   uint64_t sol_full[kSolvers];   // per SOLVER, not per slot: a waiter may lag its barrier by one phase at most, and a
                                  // solver's consecutive rows are kSolvers / kSlots uses of a slot apart
@@ -124,7 +125,7 @@ __device__ __forceinline__ void cp_async16_raw(uint32_t smem_dst, uint64_t gsrc)
 
 __device__ __noinline__ void gather_role(uint32_t stages, Bars* bars, uint8_t* gscratch, const Range* rg,
                                          const int32_t* __restrict__ colidx, const uint32_t* __restrict__ vals_hl,
-                                         const uint8_t* __restrict__ src_hl, int zero_row,
+                                         const float* __restrict__ vals_sc, const uint8_t* __restrict__ src_hl, int zero_row,
                                          const int64_t* __restrict__ chunk_pos, const int32_t* __restrict__ chunk_cnt,
                                          int gw, int lane) {
   const int t_sub = lane >> 4, piece = lane & 15;
@@ -181,6 +182,7 @@ __device__ __noinline__ void gather_role(uint32_t stages, Bars* bars, uint8_t* g
   }
   const uint64_t srcb = reinterpret_cast<uint64_t>(src_hl) + (uint64_t)piece * 16u;
   const uint32_t rdst = 2 * kBlk + (uint32_t)lane * kRowBytes + (uint32_t)((lane & 7) << 4);
+  const uint32_t sdst = 2 * kBlk + (uint32_t)lane * kRowBytes + (uint32_t)((7 ^ (lane & 7)) << 4);   // a chunk no MMA reads
   uint32_t g = 0, s = (uint32_t)gw, u = 0;   // chunks issued, stage, ring wraps
 #ifdef HALS_WS_PROFILE
   long long w_free = 0, t_iss = 0, t_fill = 0;
@@ -217,6 +219,10 @@ __device__ __noinline__ void gather_role(uint32_t stages, Bars* bars, uint8_t* g
         const bool ok = lane < cnt;
         const uint32_t* rp = vals_hl + pos + (ok ? lane : 0);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(st + rdst), "l"(rp), "r"(ok ? 4 : 0) : "memory");
+        if (vals_sc != nullptr) {          // implicit mode: sqrt(alpha |r|) of rating `lane`, read by the scaler warp
+          const float* sp = vals_sc + pos + (ok ? lane : 0);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(st + sdst), "l"(sp), "r"(ok ? 4 : 0) : "memory");
+        }
       }
       cp_async_mbar_arrive_noinc(&bars->st_full[s]);
       WS_ACC(t_iss);
@@ -235,10 +241,57 @@ __device__ __noinline__ void gather_role(uint32_t stages, Bars* bars, uint8_t* g
 #endif
 }
 
+// ---- implicit mode (Hu-Koren): rescale a landed stage in place, row t (= lane) by sqrt(c_t), c = alpha |r| ----------
+// s = sqrt(c) (h + l) in fp32, re-split into bf16 hi/lo: the SAME two MMAs then build sum c y y^T, and the rating column
+// (which carries (1 + c) / sqrt(c) where r > 0) gives b = sum_{r>0} (1 + c) y.  See als_ws128.cu for the rank-128 twin.
+__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ f32x2 unpack_bf16x2(uint32_t w) {             // (element 0, element 1) as fp32
+  return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __noinline__ void scaler_role(uint32_t stages, Bars* bars, const Range* rg, int lane) {
+  const int64_t k_lo = rg->chunk_lo, k_hi = rg->chunk_hi;
+  const uint32_t rowo = (uint32_t)lane * kRowBytes, x = (uint32_t)(lane & 7);
+  const f32x2 one2 = pack2(1.f, 1.f), mone2 = pack2(-1.f, -1.f);
+  uint32_t s = 0, su = 0;
+  for (int64_t k = k_lo; k < k_hi; ++k) {
+    umma::mbar_wait(&bars->st_full[s], su & 1);
+    const uint32_t st = stages + s * kStageBytes;
+    const float sc = lds32(st + 2 * kBlk + rowo + ((7u ^ x) << 4));
+    const f32x2 sc2 = pack2(sc, sc);
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {                       // the eight 16-byte chunks of row t: h in block 0, l in block 1
+      const uint32_t off = st + rowo + ((((uint32_t)i) ^ x) << 4);
+      const float4 hv = lds128(off), lv = lds128(off + kBlk);
+      const uint32_t hw[4] = {__float_as_uint(hv.x), __float_as_uint(hv.y), __float_as_uint(hv.z), __float_as_uint(hv.w)};
+      const uint32_t lw[4] = {__float_as_uint(lv.x), __float_as_uint(lv.y), __float_as_uint(lv.z), __float_as_uint(lv.w)};
+      uint32_t oh[4], ol[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const f32x2 y = ffma2(unpack_bf16x2(hw[j]), one2, unpack_bf16x2(lw[j]));
+        const f32x2 v = fmul2(y, sc2);
+        oh[j] = cvt_bf16x2(hi2(v), lo2(v));
+        const f32x2 r = ffma2(unpack_bf16x2(oh[j]), mone2, v);
+        ol[j] = cvt_bf16x2(hi2(r), lo2(r));
+      }
+      sts128(off, __uint_as_float(oh[0]), __uint_as_float(oh[1]), __uint_as_float(oh[2]), __uint_as_float(oh[3]));
+      sts128(off + kBlk, __uint_as_float(ol[0]), __uint_as_float(ol[1]), __uint_as_float(ol[2]), __uint_as_float(ol[3]));
+    }
+    umma::fence_proxy_async();                          // generic-proxy writes -> the tensor core's async-proxy reads
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(&bars->st_scaled[s]);
+    if (++s == (uint32_t)kStages) { s = 0; ++su; }
+  }
+}
+
 // ---- M: MMA issue (whole warp walks the chunk table, lane 0 issues) --------------------------------------
 __device__ __noinline__ void mma_role(uint32_t sbase, uint32_t tmem, Bars* bars, const Range* rg,
-                                      const int32_t* __restrict__ chunk_cnt, int lane) {
+                                      const int32_t* __restrict__ chunk_cnt, bool scaled, int lane) {
   constexpr uint32_t idesc = umma::make_instr_desc(umma::kFmtBF16, true, true, 128, kN);
+  uint64_t* const ready = scaled ? bars->st_scaled : bars->st_full;
   const int64_t k_lo = rg->chunk_lo, k_hi = rg->chunk_hi;
   uint32_t s = 0, su = 0, b = 0, bu = 0;
   bool first = true;                       // the next chunk starts a new item (= a new accumulator)
@@ -262,7 +315,7 @@ __device__ __noinline__ void mma_role(uint32_t sbase, uint32_t tmem, Bars* bars,
           if (bu > 0) { WS_T0(); umma::mbar_wait(&bars->acc_free[b], (bu - 1) & 1); WS_ACC(w_acc); }
           umma::fence_after_sync();
         }
-        { WS_T0(); umma::mbar_wait(&bars->st_full[s], su & 1); WS_ACC(w_full); }
+        { WS_T0(); umma::mbar_wait(&ready[s], su & 1); WS_ACC(w_full); }
         WS_T0();
         const uint32_t td = tmem + b * kAccCols;
         const uint64_t so = (uint64_t)((s * kStageBytes) >> 4);       // the descriptors' start-address field counts 16 bytes
@@ -289,7 +342,7 @@ __device__ __noinline__ void mma_role(uint32_t sbase, uint32_t tmem, Bars* bars,
 }
 
 // ---- D: drain TMEM -> hand-over slot -----------------------------------------------------------------
-__device__ __noinline__ void drain_role(uint32_t slots, uint32_t tmem, Bars* bars, const Range* rg, int tid) {
+__device__ __noinline__ void drain_role(uint32_t slots, uint32_t tmem, Bars* bars, const Range* rg, int nsolv, int tid) {
   const int warp = tid >> 5;
   const int64_t n_rows = rg->item_hi - rg->item_lo;
   uint32_t b = 0, bu = 0, sl = 0, slu = 0, sv = 0;
@@ -322,7 +375,7 @@ __device__ __noinline__ void drain_role(uint32_t slots, uint32_t tmem, Bars* bar
     umma::mbar_arrive(&bars->sol_full[sv]);
     if (++b == (uint32_t)kAcc) { b = 0; ++bu; }
     if (++sl == (uint32_t)kSlots) { sl = 0; ++slu; }
-    if (++sv == (uint32_t)kSolvers) sv = 0;
+    if (++sv == (uint32_t)nsolv) sv = 0;
   }
 #ifdef HALS_WS_PROFILE
   if (tid == 0 && blockIdx.x == 1) printf("D: wait_acc_full %lld tmem_ld %lld wait_slot_free %lld\n", w_acc, t_ld, w_slot);
@@ -470,7 +523,8 @@ __device__ __forceinline__ void back_block(const f32x2 (&R)[36], f32x2 (&x2)[8],
 __device__ __noinline__ void solver_role(uint32_t slots, uint32_t scratch, Bars* bars, float* __restrict__ dst,
                                          __nv_bfloat16* __restrict__ dst_hl, float* __restrict__ workspace, float reg,
                                          const int32_t* __restrict__ item_row, const int32_t* __restrict__ item_len,
-                                         const int32_t* __restrict__ item_slot, const Range* rg, int w, int lane) {
+                                         const int32_t* __restrict__ item_slot, const float* __restrict__ gram_tiles,
+                                         const Range* rg, int nsolv, int w, int lane) {
   const int ti = lane >> 3, tj = lane & 7;
   const uint32_t P = scratch, Y = P + 512, DI = Y + 256, T = DI + 256, RH = T + 256;
   const int64_t n_items = rg->item_hi;
@@ -483,10 +537,10 @@ __device__ __noinline__ void solver_role(uint32_t slots, uint32_t scratch, Bars*
   int row_n = 0, len_n = 0, slot_n = -1;
   if (it < n_items) { row_n = __ldg(item_row + it); len_n = __ldg(item_len + it); slot_n = __ldg(item_slot + it); }
   uint32_t mine = 0;                     // rows this solver has taken
-  for (uint32_t i = (uint32_t)w; it < n_items; i += kSolvers, it += kSolvers, ++mine) {
+  for (uint32_t i = (uint32_t)w; it < n_items; i += nsolv, it += nsolv, ++mine) {
     const int row = row_n, len = len_n, wslot = slot_n;
     {
-      const int64_t nx = it + kSolvers;
+      const int64_t nx = it + nsolv;
       if (nx < n_items) { row_n = __ldg(item_row + nx); len_n = __ldg(item_len + nx); slot_n = __ldg(item_slot + nx); }
     }
     const uint32_t sl = i % kSlots;
@@ -526,6 +580,15 @@ __device__ __noinline__ void solver_role(uint32_t slots, uint32_t scratch, Bars*
             if (q == c) v[h] += (ti + 4 * h == tj) ? lam : 0.f;
           }
           R[tri(q, c)] = pack2(v[0], v[1]);
+        }
+      }
+      if (gram_tiles != nullptr) {                           // implicit: + Y^T Y, already in this lane's tile order
+        const float4* gp = reinterpret_cast<const float4*>(gram_tiles) + lane * 18;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+          const float4 g = __ldg(gp + i);
+          R[2 * i] = ffma2(pack2(g.x, g.y), pack2(1.f, 1.f), R[2 * i]);
+          R[2 * i + 1] = ffma2(pack2(g.z, g.w), pack2(1.f, 1.f), R[2 * i + 1]);
         }
       }
       const uint32_t ob = (uint32_t)(ti + 8 * tj) * 4u;
@@ -583,6 +646,7 @@ __device__ __noinline__ void solver_role(uint32_t slots, uint32_t scratch, Bars*
 
 __global__ void __launch_bounds__(kThreads, 1)
 als_ws64_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict__ vals_hl,
+                const float* __restrict__ vals_sc, const float* __restrict__ gram_tiles,
                 const __nv_bfloat16* __restrict__ src_hl, float* __restrict__ dst, float reg,
                 const int32_t* __restrict__ item_row, const int32_t* __restrict__ item_len,
                 const int32_t* __restrict__ item_slot, const int64_t* __restrict__ item_chunk0,
@@ -597,7 +661,11 @@ als_ws64_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == kWarpDrain) umma::tmem_alloc(&tmem_slot, kAcc * kAccCols);
   if (tid == 32) {
-    for (int s = 0; s < kStages; ++s) { umma::mbar_init(&bars.st_full[s], 32); umma::mbar_init(&bars.st_free[s], 1); }
+    for (int s = 0; s < kStages; ++s) {
+      umma::mbar_init(&bars.st_full[s], 32);
+      umma::mbar_init(&bars.st_free[s], 1);
+      umma::mbar_init(&bars.st_scaled[s], 1);
+    }
     for (int b = 0; b < kAcc; ++b) { umma::mbar_init(&bars.acc_full[b], 1); umma::mbar_init(&bars.acc_free[b], 128); }
     for (int s = 0; s < kSlots; ++s) umma::mbar_init(&bars.slot_free[s], 1);
     for (int s = 0; s < kSolvers; ++s) umma::mbar_init(&bars.sol_full[s], 128);
@@ -633,16 +701,21 @@ als_ws64_kernel(const int32_t* __restrict__ colidx, const uint32_t* __restrict__
   const uint32_t scratch = slots + kSlots * kSlotBytes;
   uint8_t* gscratch = base + kStages * kStageBytes + kSlots * kSlotBytes + kSolvers * kScratchBytes;
 
+  // implicit mode: the last solver warp becomes the scaler (eight solvers instead of nine)
+  const bool implicit = vals_sc != nullptr;
+  const int nsolv = implicit ? kSolvers - 1 : kSolvers;
   if (warp >= kWarpDrain) {
-    drain_role(slots, tmem, &bars, &range, tid - kWarpDrain * 32);
+    drain_role(slots, tmem, &bars, &range, nsolv, tid - kWarpDrain * 32);
   } else if (warp >= kWarpGather && warp < kWarpMma) {
-    gather_role(sbase, &bars, gscratch + (warp - kWarpGather) * kGatherScratch, &range, colidx, vals_hl,
+    gather_role(sbase, &bars, gscratch + (warp - kWarpGather) * kGatherScratch, &range, colidx, vals_hl, vals_sc,
                 reinterpret_cast<const uint8_t*>(src_hl), zero_row, chunk_pos, chunk_cnt, warp - kWarpGather, lane);
   } else if (warp == kWarpMma) {
-    mma_role(sbase, tmem, &bars, &range, chunk_cnt, lane);
-  } else {
+    mma_role(sbase, tmem, &bars, &range, chunk_cnt, implicit, lane);
+  } else if (warp - kWarpSolver < nsolv) {
     solver_role(slots, scratch + (uint32_t)(warp - kWarpSolver) * kScratchBytes, &bars, dst, dst_hl, workspace, reg, item_row,
-                item_len, item_slot, &range, warp - kWarpSolver, lane);
+                item_len, item_slot, gram_tiles, &range, nsolv, warp - kWarpSolver, lane);
+  } else {
+    scaler_role(sbase, &bars, &range, lane);
   }
 #ifdef HALS_WS_PROFILE
   const long long t_role = clock64() - t_cta0;
@@ -664,7 +737,7 @@ __global__ void __launch_bounds__(128)
 als_reduce_solve64_warp_kernel(const float* __restrict__ workspace, float* __restrict__ dst,
                                __nv_bfloat16* __restrict__ dst_hl, float reg, const int32_t* __restrict__ long_row,
                                const int32_t* __restrict__ long_slot0, const int32_t* __restrict__ long_nseg, int final_stride_1,
-                               int final_stride_2) {
+                               int final_stride_2, const float* __restrict__ gram) {
   constexpr int SF = K * K + K + 4;
   __shared__ __align__(16) float sA[SF];
   __shared__ __align__(16) uint8_t sScratch[kScratchBytes];
@@ -693,7 +766,7 @@ als_reduce_solve64_warp_kernel(const float* __restrict__ workspace, float* __res
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int m = ti + 4 * h + 8 * q, n = tj + 8 * c;
-        v[h] = sA[m * K + n] + (m == n ? lam : 0.f);
+        v[h] = sA[m * K + n] + (m == n ? lam : 0.f) + (gram != nullptr ? __ldg(gram + m * K + n) : 0.f);
       }
       R[tri(q, c)] = pack2(v[0], v[1]);
     }
@@ -801,8 +874,21 @@ int als_count_positive(const float* vals, const int64_t* item_begin, const int32
 // engine keeps the factors in this form across half-steps: every solved row is written as fp32 (dst) AND as its
 // bf16 hi|lo split (dst_hl, same row indexing as dst), so no split pass is needed and a sharded run all-gathers the
 // split rows in place.
+// Y^T Y ([64][64]) -> the one-warp solver's lane-tile order: tiles[lane][tri(q, c)] = (G[ti + 8q][tj + 8c],
+// G[ti + 4 + 8q][tj + 8c]), lane = 8 ti + tj.
+__global__ void gram_to_tiles64_kernel(const float* __restrict__ G, float* __restrict__ tiles) {
+  const int lane = threadIdx.x, ti = lane >> 3, tj = lane & 7;
+  for (int q = 0; q < 8; ++q)
+    for (int c = 0; c <= q; ++c)
+      for (int h = 0; h < 2; ++h)
+        tiles[lane * 72 + ws64::tri(q, c) * 2 + h] = G[(ti + 4 * h + 8 * q) * ws64::K + tj + 8 * c];
+}
+
+// gram != nullptr selects implicit feedback (the plan must carry vals_scale / item_npos packed for the caller's alpha;
+// gram_tiles = 9,216 bytes of scratch).
 int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const float* src, int64_t n_src, float* dst,
-                       float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl, cudaStream_t st) {
+                       float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl,
+                       const float* gram, float* gram_tiles, cudaStream_t st) {
   using namespace ws64;
   __nv_bfloat16* hl = reinterpret_cast<__nv_bfloat16*>(split_buf);
   HALS_REQUIRE(n_src < (int64_t)1 << 31, "at most 2^31 - 1 source rows");
@@ -818,10 +904,17 @@ int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const flo
   static_assert(kStages * kStageBytes + kSlots * kSlotBytes + kSolvers * kScratchBytes + 2 * kGatherScratch + 1024 <= 227 * 1024 - 1024,
                 "shared memory budget");
   HALS_CUDA(cudaFuncSetAttribute(als_ws64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool implicit = gram != nullptr;
+  if (implicit) {
+    HALS_REQUIRE(plan->vals_scale && plan->item_npos && gram_tiles, "implicit mode needs the plan's vals_scale / item_npos");
+    gram_to_tiles64_kernel<<<1, 32, 0, st>>>(gram, gram_tiles);
+    HALS_LAUNCH_CHECK();
+  }
   int64_t grid = sm_count();
   if (grid > plan->n_items) grid = plan->n_items;
-  als_ws64_kernel<<<(unsigned)grid, kThreads, smem, st>>>(colidx, vals_hl, hl, dst, reg, plan->item_row, plan->item_len,
-                                                         plan->item_slot, plan->item_chunk0, plan->item_cost0,
+  als_ws64_kernel<<<(unsigned)grid, kThreads, smem, st>>>(colidx, vals_hl, implicit ? plan->vals_scale : nullptr,
+                                                         implicit ? gram_tiles : nullptr, hl, dst, reg, plan->item_row,
+                                                         implicit ? plan->item_npos : plan->item_len, plan->item_slot, plan->item_chunk0, plan->item_cost0,
                                                          plan->chunk_pos, plan->chunk_cnt, plan->n_items, (int)n_src, slots,
                                                          reinterpret_cast<__nv_bfloat16*>(dst_hl));
   HALS_LAUNCH_CHECK();
@@ -829,7 +922,8 @@ int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const flo
     if (int rc = als_launch_slot_group_sum(slots, plan, K * K + K + 4, st)) return rc;
     // level strides of the slot pre-sums (als_tc.cu: kSlotGroup = 16)
     als_reduce_solve64_warp_kernel<<<(unsigned)plan->n_long_rows, 128, 0, st>>>(
-        slots, dst, reinterpret_cast<__nv_bfloat16*>(dst_hl), reg, plan->long_row, plan->long_slot0, plan->long_nseg, 16, 256);
+        slots, dst, reinterpret_cast<__nv_bfloat16*>(dst_hl), reg, plan->long_row, plan->long_slot0, plan->long_nseg, 16, 256,
+        gram);
     HALS_LAUNCH_CHECK();
   }
   return 0;

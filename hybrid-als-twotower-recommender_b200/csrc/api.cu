@@ -22,7 +22,8 @@ int als_pack_ratings_implicit(const float* vals, int64_t nnz, float alpha, uint3
 int als_count_positive(const float* vals, const int64_t* item_begin, const int32_t* item_len, int64_t n_items, int32_t* out,
                        cudaStream_t st);
 int als_half_step_ws64(const int32_t* colidx, const uint32_t* vals_hl, const float* src, int64_t n_src, float* dst,
-                       float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl, cudaStream_t st);
+                       float reg, const hals_als_plan* plan, float* slots, void* split_buf, void* dst_hl,
+                       const float* gram, float* gram_tiles, cudaStream_t st);
 int als_launch_split_bf16(const float* src, int64_t n_src, int k, void* out, cudaStream_t st);
 int als_pack_ratings(const float* vals, int64_t nnz, uint32_t* out, cudaStream_t st);
 }  // namespace hals
@@ -44,21 +45,22 @@ static size_t slot_region_bytes(int64_t n_slots, int k) {
   const size_t KP = (size_t)padded_rank(k);
   return (size_t)(n_slots > 0 ? n_slots : 0) * (KP * KP + KP + 4) * sizeof(float);
 }
-// tensor-core path: explicit feedback at ranks 64 and 128; implicit feedback at rank 128 when the plan carries the
-// operands packed for this alpha (HALS_FORCE_SIMT=1 routes everything to the SIMT path)
+// tensor-core path: ranks 64 and 128; implicit feedback when the plan carries the operands packed for this alpha (HALS_FORCE_SIMT=1 routes everything to the SIMT path)
 static bool use_tc(int k, int implicit, float alpha, const hals_als_plan* plan) {
   static const bool force_simt = [] { const char* e = getenv("HALS_FORCE_SIMT"); return e && e[0] == '1'; }();
   if (force_simt) return false;
   if (!implicit) return (k == 64 || k == 128) && plan->packed_alpha == 0.f;
-  return k == 128 && plan->vals_hl && plan->vals_scale && plan->item_npos && plan->chunk_pos && plan->packed_alpha == alpha &&
+  return (k == 64 || k == 128) && plan->vals_hl && plan->vals_scale && plan->item_npos && plan->chunk_pos && plan->packed_alpha == alpha &&
          alpha > 0.f;
 }
-constexpr size_t kGramTileBytes = 128 * 72 * sizeof(float);   // Y^T Y in the rank-128 solver's lane-tile order
+static size_t gram_tile_bytes(int k) {   // Y^T Y in the solver's lane-tile order (implicit feedback, ranks 64 / 128)
+  return k == 128 ? 128 * 72 * sizeof(float) : k == 64 ? 32 * 72 * sizeof(float) : 0;
+}
 
 extern "C" size_t hals_als_workspace_bytes(int64_t n_slots, int k, int64_t n_src) {
   // [partial (A,b,n) slots][bf16 h|l split of the source factors, tensor-core path]
   // [partial (A,b,n) slots][bf16 h|l split of the source factors + one all-zero row][Gram tiles (implicit, rank 128)]
-  return slot_region_bytes(n_slots, k) + (size_t)(n_src > 0 ? n_src : 0) * 4 * (size_t)k + 1024 + (k == 128 ? kGramTileBytes : 0);
+  return slot_region_bytes(n_slots, k) + (size_t)(n_src > 0 ? n_src : 0) * 4 * (size_t)k + 1024 + gram_tile_bytes(k);
 }
 
 // Work items: first every slice of every long row (big, uniform items first so that the
@@ -184,7 +186,7 @@ extern "C" int hals_als_half_step_split(const int32_t* colidx, int64_t m_dst, co
     return als_half_step_ws128(colidx, plan->vals_hl, nullptr, n_src, dst, reg, plan, (float*)workspace,
                                const_cast<void*>(src_hl), dst_hl, nullptr, nullptr, (cudaStream_t)stream);
   return als_half_step_ws64(colidx, plan->vals_hl, nullptr, n_src, dst, reg, plan, (float*)workspace,
-                            const_cast<void*>(src_hl), dst_hl, (cudaStream_t)stream);
+                            const_cast<void*>(src_hl), dst_hl, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int hals_als_pack_ratings(const float* vals, int64_t nnz, uint32_t* out, void* stream) {
@@ -237,8 +239,10 @@ extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, 
     void* split = reinterpret_cast<uint8_t*>(workspace) + slot_region_bytes(plan->n_slots, k);
     if (implicit) {
       float* tiles = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(split) + (size_t)n_src * 4 * (size_t)k + 1024);
-      return als_half_step_ws128(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split, nullptr, gram,
-                                 tiles, st);
+      return k == 128 ? als_half_step_ws128(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split,
+                                            nullptr, gram, tiles, st)
+                      : als_half_step_ws64(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split,
+                                           nullptr, gram, tiles, st);
     }
     if (k == 128) {
       // HALS_TC128_IMPL=groups selects the round-1 kernel (two solver groups, no chunk table)
@@ -252,7 +256,8 @@ extern "C" int hals_als_half_step(const int64_t* rowptr, const int32_t* colidx, 
     static const bool old64 = [] { const char* e = getenv("HALS_TC64_IMPL"); return e && e[0] == 'c'; }();
     if (old64 || plan->vals_hl == nullptr || plan->chunk_pos == nullptr)
       return als_half_step_tc64(colidx, vals, src, n_src, dst, reg, plan, (float*)workspace, split, st);
-    return als_half_step_ws64(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split, nullptr, st);
+    return als_half_step_ws64(colidx, plan->vals_hl, src, n_src, dst, reg, plan, (float*)workspace, split, nullptr, nullptr,
+                              nullptr, st);
   }
   return als_half_step_simt(colidx, vals, src, dst, k, reg, implicit, alpha, gram, plan, (float*)workspace, st);
 }

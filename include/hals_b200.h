@@ -87,7 +87,8 @@ typedef struct hals_als_plan {
                                 hals_als_pack_ratings once per ratings matrix.  The rank-64 tensor-core kernel
                                 copies it straight into the MMA operand; NULL selects the slower kernel that
                                 converts the fp32 ratings itself. */
-  /* Implicit feedback on the tensor cores (rank 128; optional -- without them implicit mode runs the CUDA-core kernel).
+  /* Implicit feedback on the tensor cores (ranks 64 and 128; optional -- without them implicit mode runs the CUDA-core
+   * kernel).
    * hals_als_pack_ratings_implicit fills vals_hl with (1 + c) / sqrt(c) where r > 0 (0 elsewhere) and vals_scale with
    * sqrt(c), c = alpha |r|; hals_als_plan_count_positive fills item_npos.  packed_alpha records the alpha they were
    * built for: 0 = vals_hl holds the plain ratings (explicit feedback). */

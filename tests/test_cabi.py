@@ -101,7 +101,8 @@ def test_planner_rejects_bad_input():
 
 def test_workspace_queries():
     L = nat.lib()
-    assert L.hals_als_workspace_bytes(0, 64, 0) <= 1024      # slack only (holds the all-zero row of the split buffer)
+    assert L.hals_als_workspace_bytes(0, 10, 0) <= 1024      # slack only (holds the all-zero row of the split buffer)
+    assert L.hals_als_workspace_bytes(0, 64, 0) <= 1024 + 32 * 72 * 4    # + Gram tiles (implicit, rank 64)
     assert L.hals_als_workspace_bytes(0, 128, 0) <= 1024 + 128 * 72 * 4   # + Gram tiles (implicit, rank 128)
     assert L.hals_als_sse_workspace_bytes() >= 1024 * 8
     assert L.hals_als_workspace_bytes(3, 64, 0) >= 3 * (64 * 64 + 64) * 4

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 HS_REL, HS_ABS = 2e-5, 1e-4
 # Implicit feedback: the weights c = alpha |r| (up to several hundred) worsen the conditioning of the normal equations.
-# fp32 CUDA-core build: 5e-5.  Rank 128 on the tensor cores: the rows rescaled by sqrt(c) are re-split into bf16 hi/lo
+# fp32 CUDA-core build: 5e-5.  Ranks 64 / 128 on the tensor cores: the rows rescaled by sqrt(c) are re-split into bf16 hi/lo
 # (16-17 significant bits, twice the representation error of the explicit build): 2e-4.
 IMPL_TOL = {False: dict(rel=5e-5, ab=3e-4), True: dict(rel=2e-4, ab=1e-3)}
 
@@ -90,7 +90,7 @@ def test_half_step_implicit_matches_oracle(k):
     got, _ = gpu_half_step(i, u, r, I, X, 0.05, implicit=True, alpha=40.0)
     rp, ci, v = als_oracle.coo_to_csr(i, u, r, I)
     want = c_oracle.als_half_step(rp, ci, v, X, 0.05, implicit=True, alpha=40.0)
-    assert_close(got, want, **IMPL_TOL[k == 128])
+    assert_close(got, want, **IMPL_TOL[k in (64, 128)])
 
 
 @pytest.mark.parametrize("k", [64, 128])
@@ -107,7 +107,7 @@ def test_implicit_long_rows_and_mixed_signs(k):
     assert plan.n_long > 0
     rp, ci, v = als_oracle.coo_to_csr(i, u, r, I)
     want = c_oracle.als_half_step(rp, ci, v, X, 0.05, implicit=True, alpha=15.0)
-    assert_close(got, want, **IMPL_TOL[k == 128])
+    assert_close(got, want, **IMPL_TOL[k in (64, 128)])
     again, _ = gpu_half_step(i, u, r, I, X, 0.05, implicit=True, alpha=15.0, seg_len=96)
     assert np.array_equal(got, again)
 
