@@ -62,6 +62,42 @@ class ALSFactors:
         return np.where(ok, pos, -1)
 
 
+def read_spark_als_dir(model_path):
+    """Factors of a Spark `ALSModel` directory, i.e. what the reference's save_model writes (als_model.py:116-127 ->
+    pyspark ALSModel.save): `metadata/part-00000` (one JSON line), `userFactors/*.parquet` and `itemFactors/*.parquet`
+    with the columns `id: int` and `features: array<float>`.  Returns (rank, user_ids, user_factors, item_ids,
+    item_factors) with ids sorted ascending and factors as fp32 [n, rank].  Pure host code (pyarrow)."""
+    import json
+    import pyarrow.parquet as pq
+
+    def table(name):
+        t = pq.read_table(os.path.join(model_path, name), columns=["id", "features"])
+        ids = t["id"].combine_chunks().to_numpy(zero_copy_only=False).astype(np.int64)
+        feats = t["features"].combine_chunks()
+        flat = feats.flatten().to_numpy(zero_copy_only=False).astype(np.float32)
+        if len(ids) == 0:
+            return ids, flat.reshape(0, 0)
+        k = len(flat) // len(ids)
+        if k * len(ids) != len(flat):
+            raise ValueError(f"{model_path}/{name}: feature vectors of unequal length")
+        order = np.argsort(ids, kind="stable")
+        return ids[order], np.ascontiguousarray(flat.reshape(len(ids), k)[order])
+
+    uid, uf = table("userFactors")
+    iid, itf = table("itemFactors")
+    rank = uf.shape[1] if len(uid) else itf.shape[1]
+    meta = os.path.join(model_path, "metadata", "part-00000")
+    if os.path.exists(meta):
+        with open(meta) as f:
+            md = json.loads(f.readline())
+        rank_md = md.get("rank", md.get("paramMap", {}).get("rank", rank))
+        if int(rank_md) != rank:
+            raise ValueError(f"{model_path}: metadata rank {rank_md} != stored feature length {rank}")
+    if len(uid) and len(iid) and uf.shape[1] != itf.shape[1]:
+        raise ValueError(f"{model_path}: user and item factors have different ranks")
+    return int(rank), uid, uf, iid, itf
+
+
 def _as_item_ids(all_items):
     """The reference hands the same `all_items` to both predictors (hybrid_system.py:101-102)
     although ALS wants ids and the two-tower model wants a DataFrame: accept both."""
@@ -256,18 +292,20 @@ class ALSModel:
             import torch
             if not self.initialize_spark():
                 return None
-            if os.path.isdir(model_path) and not os.path.exists(f"{model_path}.npz"):
-                # what the reference's ALSModel.save_model writes (als_model.py:116-127): a Spark ALSModel directory
-                raise ValueError(f"{model_path} is a Spark ALSModel directory (parquet userFactors/itemFactors); this "
-                                 "package stores factors as <path>.npz -- export them with numpy (ids, features) and "
-                                 "save through ALSModel.save_model, see INTEGRATION.md")
-            z = np.load(f"{model_path}.npz")
             dev = torch.device("cuda")
-            self.model = ALSFactors(int(z["rank"]), z["user_ids"], z["item_ids"],
-                                    torch.from_numpy(z["user_factors"]).to(dev),
-                                    torch.from_numpy(z["item_factors"]).to(dev),
-                                    torch.from_numpy(z["user_present"]).to(dev),
-                                    torch.from_numpy(z["item_present"]).to(dev))
+            if os.path.isdir(model_path) and not os.path.exists(f"{model_path}.npz"):
+                # a model trained and saved by the reference: a Spark ALSModel directory next to the same metadata pickle
+                rank, uid, uf, iid, itf = read_spark_als_dir(model_path)
+                self.model = ALSFactors(rank, uid, iid, torch.from_numpy(uf).to(dev), torch.from_numpy(itf).to(dev),
+                                        torch.ones(len(uid), dtype=torch.bool, device=dev),
+                                        torch.ones(len(iid), dtype=torch.bool, device=dev))
+            else:
+                z = np.load(f"{model_path}.npz")
+                self.model = ALSFactors(int(z["rank"]), z["user_ids"], z["item_ids"],
+                                        torch.from_numpy(z["user_factors"]).to(dev),
+                                        torch.from_numpy(z["item_factors"]).to(dev),
+                                        torch.from_numpy(z["user_present"]).to(dev),
+                                        torch.from_numpy(z["item_present"]).to(dev))
             with open(f"{model_path}_metadata.pkl", "rb") as f:
                 metadata = pickle.load(f)
                 self.rank = metadata["rank"]

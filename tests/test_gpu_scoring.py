@@ -420,3 +420,33 @@ def test_hyperparameter_tuning_grid_search():
     with contextlib.redirect_stdout(log):
         assert ttm.hyperparameter_tuning(bad, grid, val_size=0.25, random_state=7) is None
     assert "ids must lie in" in log.getvalue()
+
+
+@pytest.mark.gpu
+def test_load_model_reads_a_checkpoint_written_by_the_reference(tmp_path):
+    """ALSModel.load_model on what the reference's save_model leaves behind: a Spark ALSModel directory (parquet factors)
+    plus `<path>_metadata.pkl` (src/als_model.py:116-136).  Predictions must be the dot products of the stored factors."""
+    import json
+    import pickle
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    pkg, nat, _ = _pkg()
+    rng = np.random.default_rng(3)
+    rank, uid, iid = 10, np.array([4, 9, 17, 30]), np.arange(100, 140)
+    UF, IF = rng.standard_normal((len(uid), rank)).astype(np.float32), rng.standard_normal((len(iid), rank)).astype(np.float32)
+    root = tmp_path / "als"
+    (root / "metadata").mkdir(parents=True)
+    (root / "metadata" / "part-00000").write_text(json.dumps({"class": "org.apache.spark.ml.recommendation.ALSModel", "rank": rank}) + "\n")
+    for name, ids, f in (("userFactors", uid, UF), ("itemFactors", iid, IF)):
+        (root / name).mkdir()
+        perm = rng.permutation(len(ids))
+        pq.write_table(pa.table({"id": pa.array(ids[perm].astype(np.int32)),
+                                 "features": pa.array([r.tolist() for r in f[perm]], type=pa.list_(pa.float32()))}),
+                       root / name / "part-00000.snappy.parquet")
+    with open(f"{root}_metadata.pkl", "wb") as f:
+        pickle.dump({"rank": rank, "max_iter": 10, "reg_param": 0.1, "global_mean": 3.5, "item_features": {}}, f)
+    m = pkg.ALSModel().load_model(str(root))
+    assert m is not None and m.rank == rank and m.global_mean == 3.5
+    preds = dict(m.predict_for_user(17, list(iid[:7])))
+    want = IF[:7] @ UF[2]
+    assert np.allclose([preds[i] for i in iid[:7]], want, atol=1e-5)

@@ -3,6 +3,7 @@
 The plan stands where Spark cuts ratings into in-blocks (ALS.scala makeBlocks, reached from
 src/als_model.py:62); the kernels only ever see its arrays."""
 import numpy as np
+import pytest
 import torch
 
 from hybrid_als_twotower_recommender_b200 import _native as nat
@@ -52,3 +53,39 @@ def test_big_shard_keeps_the_default_and_explicit_value_wins():
     plan = AlsPlanHandle(_shard([5000, 10, 0, 70]), 64, seg_len=64, device="cpu")
     assert plan.seg_len == 64 and plan.n_long == 2
     _check_plan(plan, [5000, 10, 0, 70])
+
+
+def test_spark_als_model_directory_is_readable(tmp_path):
+    """A checkpoint written by the reference (pyspark ALSModel.save, src/als_model.py:116-127): metadata JSON +
+    userFactors / itemFactors parquet (id int, features array<float>), possibly in several part files and in any row
+    order.  read_spark_als_dir returns sorted ids and fp32 factor tables."""
+    import json
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from hybrid_als_twotower_recommender_b200.als_model import read_spark_als_dir
+    rng = np.random.default_rng(0)
+    rank = 6
+    root = tmp_path / "als"
+    (root / "metadata").mkdir(parents=True)
+    (root / "metadata" / "part-00000").write_text(json.dumps({"class": "org.apache.spark.ml.recommendation.ALSModel",
+                                                              "sparkVersion": "3.5.1", "rank": rank, "paramMap": {}}) + "\n")
+    (root / "metadata" / "_SUCCESS").write_text("")
+    want = {}
+    for name, ids in (("userFactors", rng.permutation(np.arange(3, 40, 3))), ("itemFactors", rng.permutation(50)[:17])):
+        f = rng.standard_normal((len(ids), rank)).astype(np.float32)
+        want[name] = (ids, f)
+        (root / name).mkdir()
+        (root / name / "_SUCCESS").write_text("")
+        half = len(ids) // 2
+        for part, sl in enumerate((slice(0, half), slice(half, None))):
+            t = pa.table({"id": pa.array(ids[sl].astype(np.int32)),
+                          "features": pa.array([row.tolist() for row in f[sl]], type=pa.list_(pa.float32()))})
+            pq.write_table(t, root / name / f"part-{part:05d}-x.snappy.parquet")
+    r, uid, uf, iid, itf = read_spark_als_dir(str(root))
+    assert r == rank and uf.dtype == np.float32 and uf.shape == (len(uid), rank) and itf.shape == (len(iid), rank)
+    for (ids, f), (gi, gf) in ((want["userFactors"], (uid, uf)), (want["itemFactors"], (iid, itf))):
+        o = np.argsort(ids)
+        assert np.array_equal(gi, ids[o]) and np.array_equal(gf, f[o])
+    (root / "metadata" / "part-00000").write_text(json.dumps({"rank": rank + 1}) + "\n")
+    with pytest.raises(ValueError):
+        read_spark_als_dir(str(root))
