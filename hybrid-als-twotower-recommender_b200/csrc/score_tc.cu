@@ -17,11 +17,12 @@
 // eps_u), i.e. no rejected item could belong to the answer; otherwise the user is flagged and
 // re-done by the exact SIMT kernel (score_simt.cu) -- on the GPU, never on the host.
 //
-// Kernel shape: CTA = 128 users (UMMA M) x a contiguous item range, 10 warps:
+// Kernel shape: CTA = 128 users (UMMA M) x a contiguous item range, 10 warps (pass 1) or 18 warps (pass 2):
 //   warp 0    TMA producer: user tile once, item K-blocks ([256 x 64] bf16, 128B swizzle) through a 4-stage ring
 //   warp 1    MMA issuer: 4 x tcgen05.mma (M=128, N=256, K=16) per K-block, accumulators double-buffered in TMEM
 //             (2 x 256 columns; pass 1 scores the two models as two consecutive accumulator jobs per item tile)
-//   warps 2-9 epilogue, two warps per TMEM lane quarter (each takes half of the tile's columns): tcgen05.ld 32 / 64
+//   warps 2.. epilogue, PARTS warps per TMEM lane quarter (each takes 1/PARTS of the tile's columns; pass 1: 2, pass 2: 4,
+//             one candidate stream per part): tcgen05.ld 32 / 64
 //             columns per step with the next load in flight, thread = user row, FMNMX3 chains per 8-column octet
 //             against the row threshold held in a register; only octets with a survivor walk their columns.
 #include <cuda_bf16.h>
@@ -35,18 +36,19 @@ namespace hals {
 
 constexpr int kStM = 128;
 constexpr int kStRing = 4;
+// Epilogue warps per TMEM lane quarter (PARTS): each takes 1/PARTS of a tile's columns and, in pass 2, feeds its own
+// candidate stream.  With 2 warps per scheduler the epilogue is latency-bound (38 % of its samples are fixed-latency
+// waits, ncu round 2).  Pass 2 runs 4 parts = 16 epilogue warps at 96 registers; what makes that pay is halving the
+// kept set and the buffer of a stream with it (4 streams x keep 64 see the same threshold -- the global rank-256 score
+// -- and the same number of survivors as 2 x 128; a first try with 4 x 128 was 19 % SLOWER: 1.8x the survivors).  Pass 1
+// keeps 2 parts (4 measured slower there: 717 vs 632 ms on the 1 M x 1.25 M leg, its lists need the registers).
 #ifndef HALS_SCORE_PARTS
-#define HALS_SCORE_PARTS 2
+#define HALS_SCORE_PARTS 4
 #endif
-// Epilogue warps per TMEM lane quarter; each takes 1/kStParts of a tile's columns and feeds its own candidate stream.
-// 2 warps per scheduler leave the epilogue latency-bound (38 % of its samples are fixed-latency waits, ncu round 2), but
-// 4 (16 epilogue warps at 96 registers, twice the candidate streams) measured SLOWER on the 1M x 1.25M leg: extrema
-// pass 717 vs 632 ms, blend + top-k pass 879 vs 738 ms -- the extra streams cost more compactions and exact re-scoring
-// than the extra warps hide.
-constexpr int kStParts = HALS_SCORE_PARTS;
-static_assert(kStParts == 2 || kStParts == 4, "column parts per tile");
-constexpr int kStEpiWarps = 4 * kStParts;
-constexpr int kStThreads = 64 + 32 * kStEpiWarps;
+constexpr int kStParts1 = 2;                   // pass 1
+constexpr int kStParts2 = HALS_SCORE_PARTS;    // pass 2
+static_assert(kStParts2 == 2 || kStParts2 == 4, "column parts per tile");
+constexpr int kStPartsMax = kStParts1 > kStParts2 ? kStParts1 : kStParts2;
 constexpr int kStExC = 4;            // extrema candidates per list
 #ifndef HALS_SCORE_W
 #define HALS_SCORE_W 64              // columns per filter step of pass 2 (a candidate buffer keeps W slots free; 32: 5 % slower)
@@ -138,8 +140,8 @@ __device__ __noinline__ int compact_row(uint64_t* buf, int count, int keep, int 
   return topk_select_compact<CAP>(buf, count, keep, lane, thr_out);
 }
 
-template <int PASS, int BN, int CAP>
-__global__ void __launch_bounds__(kStThreads, 1)
+template <int PASS, int BN, int CAP, int PARTS>
+__global__ void __launch_bounds__(64 + 128 * PARTS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i, ScoreTcArgs A,
                 float* __restrict__ ex_val /* [splits][U][4][4] */, int32_t* __restrict__ ex_idx,
                 uint64_t* __restrict__ cand /* [splits][U][CAP] */, int32_t* __restrict__ cand_cnt,
@@ -168,7 +170,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
   if (tid == 0) {
     for (int s = 0; s < kStRing; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
     umma::mbar_init(&a_full, 1);
-    for (int b = 0; b < 2; ++b) { umma::mbar_init(&tmem_full[b], 1); umma::mbar_init(&tmem_empty[b], kStEpiWarps); }
+    for (int b = 0; b < 2; ++b) { umma::mbar_init(&tmem_full[b], 1); umma::mbar_init(&tmem_empty[b], 4 * PARTS); }
     umma::mbar_fence_init();
     tma::prefetch_map(&map_u);
     tma::prefetch_map(&map_i);
@@ -244,8 +246,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
     // ------------------------------------------------------------ epilogue: thread = user row
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;                   // which part of the tile's columns
-    const int vs = split * kStParts + half;             // candidate stream ("virtual split") of this thread
-    constexpr int HB = BN / kStParts;
+    const int vs = split * PARTS + half;                // candidate stream ("virtual split") of this thread
+    constexpr int HB = BN / PARTS;
     const int r = q * 32 + lane;
     const int64_t u = u0 + r;
     const bool live = u < A.n_users;
@@ -292,7 +294,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
           // instruction-fetch stalls (ncu, round 2).
           // (four warps per scheduler: no register double buffer -- the other warps cover the tcgen05.ld latency and the
           //  two candidate lists per model need the registers)
-          constexpr bool kDouble = kStParts < 4;
+          constexpr bool kDouble = PARTS < 4;
           constexpr int NB = kDouble ? 2 : 1;
           float vv[NB][32];
           if (kDouble) umma::tmem_ld32_issue(tbase + half * HB, vv[0]);
@@ -345,23 +347,30 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant
       } else {
         // W columns per step (two tcgen05.ld x32 in flight per buffer when the candidate buffer leaves room for 64
         // new keys): more independent FMNMX3 chains per wait, half as many waits, branches and ballots
-        constexpr int W = (CAP >= 256 && kStParts == 2) ? HALS_SCORE_W : 32;
+        constexpr int W = (CAP >= 256 && PARTS == 2) ? HALS_SCORE_W : 32;   // (4 parts, one 64-column step: measured slower)
         constexpr int G2 = HB / W;
-        static_assert(G2 % 2 == 0, "groups are processed in pairs");
-        float vv[2][W];
+        constexpr int NB = G2 >= 2 ? 2 : 1;
+        static_assert(G2 % NB == 0, "groups are processed in pairs");
+        float vv[NB][W];
+        if (NB == 2) {
 #pragma unroll
-        for (int x = 0; x < W / 32; ++x) umma::tmem_ld32_issue(tbase + half * HB + 32 * x, vv[0] + 32 * x);
+          for (int x = 0; x < W / 32; ++x) umma::tmem_ld32_issue(tbase + half * HB + 32 * x, vv[0] + 32 * x);
+        }
 #pragma unroll 1
-        for (int gp = 0; gp < G2; gp += 2) {
+        for (int gp = 0; gp < G2; gp += NB) {
 #pragma unroll
-        for (int gb = 0; gb < 2; ++gb) {
+        for (int gb = 0; gb < NB; ++gb) {
           const int g = gp + gb;
           const int c0 = half * HB + g * W;
+          if (NB == 1) {
+#pragma unroll
+            for (int x = 0; x < W / 32; ++x) umma::tmem_ld32_issue(tbase + c0 + 32 * x, vv[0] + 32 * x);
+          }
 #pragma unroll
           for (int x = 0; x < W / 32; ++x) umma::tmem_wait_ld_dep(vv[gb] + 32 * x);
-          if (g + 1 < G2) {
+          if (NB == 2 && g + 1 < G2) {
 #pragma unroll
-            for (int x = 0; x < W / 32; ++x) umma::tmem_ld32_issue(tbase + c0 + W + 32 * x, vv[gb ^ 1] + 32 * x);
+            for (int x = 0; x < W / 32; ++x) umma::tmem_ld32_issue(tbase + c0 + W + 32 * x, vv[(gb + 1) % NB] + 32 * x);
           }
           const float (&v)[W] = vv[gb];
           // Octet maxima (FMNMX3 chains) against the row threshold.  Survivors are ~0.4% of the items: most lanes
@@ -665,6 +674,15 @@ TcPlan make_plan(int64_t n_users, int64_t n_items, int ka, int kt, int topk) {
     if (want < 64) want = 64;
     p.keep = want < p.cap / 2 ? want : p.cap / 2;
   }
+  if (kStParts2 == 4) {
+    // four streams per row instead of two: half the kept set and half the buffer per stream.  The union still reaches
+    // the global rank ~4 keep (the verification margin is unchanged) and a stream holds its share of the top-k with
+    // overwhelming probability (k = 100: 25 +- 4.3 expected per stream against 64 kept); an adversarial item order
+    // that defeats this fails the verification and is re-run exactly, as always.
+    if (p.cap > 128) p.cap /= 2;
+    p.keep = p.keep / 2 < 32 ? 32 : p.keep / 2;
+    if (p.keep > p.cap / 2) p.keep = p.cap / 2;
+  }
   // the tensor-core path pays off once the tile grid can fill the GPU; tiny calls stay on the exact SIMT path
   p.use_tc = !force_simt && tma::encode_fn() != nullptr && n_items >= 2048 && n_users * n_items >= (int64_t)1 << 22;
   const int64_t user_tiles = (n_users + kStM - 1) / kStM;
@@ -693,7 +711,7 @@ TcPlan make_plan(int64_t n_users, int64_t n_items, int ka, int kt, int topk) {
   p.splits = (int)((n_items + p.items_per_split - 1) / p.items_per_split);
   if (p.splits < 1) p.splits = 1;
   size_t o = 0;
-  const size_t su = (size_t)kStParts * (size_t)p.splits * (size_t)n_users;   // kStParts candidate streams (column parts) per split
+  const size_t su = (size_t)kStPartsMax * (size_t)p.splits * (size_t)n_users;   // candidate streams (column parts) per split
   {
     const int tk = topk > 0 ? topk : 1;
     const size_t plain = score_simt_workspace_bytes(n_users, n_items, tk);
@@ -721,13 +739,13 @@ TcPlan make_plan(int64_t n_users, int64_t n_items, int ka, int kt, int topk) {
   return p;
 }
 
-template <int PASS, int BN, int CAP>
+template <int PASS, int BN, int CAP, int PARTS>
 int launch_tc(const CUtensorMap& mu, const CUtensorMap& mi, const ScoreTcArgs& A, int nkb, float* exv, int32_t* exi,
               uint64_t* cand, int32_t* cnt, float* thr, cudaStream_t st) {
   const size_t smem = (size_t)nkb * kStM * 128 + (size_t)kStRing * BN * 128 + 1024;
-  HALS_CUDA(cudaFuncSetAttribute(score_tc_kernel<PASS, BN, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HALS_CUDA(cudaFuncSetAttribute(score_tc_kernel<PASS, BN, CAP, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((A.n_users + kStM - 1) / kStM), (unsigned)A.n_splits);
-  score_tc_kernel<PASS, BN, CAP><<<grid, kStThreads, smem, st>>>(mu, mi, A, exv, exi, cand, cnt, thr);
+  score_tc_kernel<PASS, BN, CAP, PARTS><<<grid, 64 + 128 * PARTS, smem, st>>>(mu, mi, A, exv, exi, cand, cnt, thr);
   HALS_LAUNCH_CHECK();
   return 0;
 }
@@ -777,9 +795,9 @@ extern "C" int hals_score_extrema(const float* Ua, int64_t ua_stride, const floa
       !tma::make_bf16_rowmajor_map(&mi, ib, (uint64_t)n_items, (uint64_t)p.Kp, kTcBN))
     return fail(HALS_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", __func__);
   ScoreTcArgs A{p.nkb_a, p.nkb_t, n_users, n_items, p.items_per_split, p.splits, p.keep, 0};
-  if (int rc = launch_tc<1, kTcBN, 128>(mu, mi, A, p.nkb_a + p.nkb_t, (float*)(W + p.off_exv), (int32_t*)(W + p.off_exi),
+  if (int rc = launch_tc<1, kTcBN, 128, kStParts1>(mu, mi, A, p.nkb_a + p.nkb_t, (float*)(W + p.off_exv), (int32_t*)(W + p.off_exi),
                                       nullptr, nullptr, nullptr, st)) return rc;
-  ExactArgs E{Ua, ua_stride, Ia, ia_stride, ka, Ut, ut_stride, It, it_stride, kt, n_users, kStParts * p.splits};
+  ExactArgs E{Ua, ua_stride, Ia, ia_stride, ka, Ut, ut_stride, It, it_stride, kt, n_users, kStParts1 * p.splits};
   score_exact_extrema_kernel<<<(unsigned)((n_users * 4 + 7) / 8), 256, 0, st>>>(
       E, (const float*)(W + p.off_exv), (const int32_t*)(W + p.off_exi), unorm, inorm, extrema, flag);
   HALS_LAUNCH_CHECK();
@@ -830,15 +848,15 @@ extern "C" int hals_score_blend_topk(const float* Ua, int64_t ua_stride, const f
     return fail(HALS_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed%s", __func__);
   ScoreTcArgs A{p.nkb_a, p.nkb_t, n_users, n_items, p.items_per_split, p.splits, p.keep, item_offset};
   int rc;
-  if (p.cap == 128) rc = launch_tc<2, kTcBN, 128>(mu, mi, A, p.nkb_a + p.nkb_t, nullptr, nullptr, cand, cnt, thr, st);
-  else if (p.cap == 256) rc = launch_tc<2, kTcBN, 256>(mu, mi, A, p.nkb_a + p.nkb_t, nullptr, nullptr, cand, cnt, thr, st);
-  else rc = launch_tc<2, kTcBN, 512>(mu, mi, A, p.nkb_a + p.nkb_t, nullptr, nullptr, cand, cnt, thr, st);
+  if (p.cap == 128) rc = launch_tc<2, kTcBN, 128, kStParts2>(mu, mi, A, p.nkb_a + p.nkb_t, nullptr, nullptr, cand, cnt, thr, st);
+  else if (p.cap == 256) rc = launch_tc<2, kTcBN, 256, kStParts2>(mu, mi, A, p.nkb_a + p.nkb_t, nullptr, nullptr, cand, cnt, thr, st);
+  else rc = launch_tc<2, kTcBN, 512, kStParts2>(mu, mi, A, p.nkb_a + p.nkb_t, nullptr, nullptr, cand, cnt, thr, st);
   if (rc) return rc;
-  const int vsplits = kStParts * p.splits;
+  const int vsplits = kStParts2 * p.splits;
   ExactArgs E{Ua, ua_stride, Ia, ia_stride, ka, Ut, ut_stride, It, it_stride, kt, n_users, vsplits};
-  int sortn = 64;
-  while (sortn < p.keep) sortn <<= 1;                   // streams leave the tensor-core kernel trimmed to `keep` keys
-  if (sortn < topk) sortn = p.cap;
+  int sortn = 64;                                       // streams leave the tensor-core kernel trimmed to `keep` keys;
+  while (sortn < p.keep || sortn < topk) sortn <<= 1;   // a stream reports up to topk of them
+  if (sortn > p.cap) sortn = p.cap;
   const int64_t slots = (int64_t)vsplits * n_users * sortn;
   (void)slots;
   score_exact_blend_kernel<<<(unsigned)(((int64_t)vsplits * n_users + 7) / 8), 256, 0, st>>>(E, extrema, w_als, w_tt, item_offset, cand, cnt, p.cap, sortn);
