@@ -76,16 +76,16 @@ typedef struct hals_als_plan {
    * more than 256 slices -- the slot pre-sum launches then cover only those rows.  0 = unknown (all long rows). */
   int64_t n_long_gt16, n_long_gt256;
   /* Chunk table (optional; hals_als_plan_chunks_host).  The ratings of work item i, cut into pieces of 32, are chunks
-   * [item_chunk0[i], item_chunk0[i+1]); the persistent rank-64 kernel gives every CTA a CONTIGUOUS range of items of
-   * equal cost (item_cost0 = prefix sum of chunks + a per-item solve / park cost) and streams its chunks. */
+   * [item_chunk0[i], item_chunk0[i+1]); the persistent rank-64 / rank-128 kernels give every CTA a CONTIGUOUS range of
+   * items of equal cost (item_cost0 = prefix sum of chunks + a per-item solve / park cost) and stream its chunks. */
   int64_t n_chunks;
   const int64_t* item_chunk0; /* [n_items+1] */
   const int64_t* item_cost0;  /* [n_items+1] */
   const int64_t* chunk_pos;   /* [n_chunks] index of the chunk's first rating (into colidx / vals)              */
   const int32_t* chunk_cnt;   /* [n_chunks] ratings left in its item at that point (<= 32: the item's last chunk) */
   const uint32_t* vals_hl;   /* optional [nnz], same order as vals: bf16(r) | bf16(r - bf16(r)) << 16, written by
-                                hals_als_pack_ratings once per ratings matrix.  The rank-64 tensor-core kernel
-                                copies it straight into the MMA operand; NULL selects the slower kernel that
+                                hals_als_pack_ratings once per ratings matrix.  The tensor-core kernels
+                                copy it straight into the MMA operand; NULL selects the slower kernel that
                                 converts the fp32 ratings itself. */
   /* Implicit feedback on the tensor cores (ranks 64 and 128; optional -- without them implicit mode runs the CUDA-core
    * kernel).
