@@ -615,14 +615,14 @@ def main():
             traffic_src = f"profiles/r02_traffic.json, captured at commit {trj.get('captured_at_commit', '?')} ({trj.get('kernel', '?')})"
     except (OSError, ValueError, KeyError):
         traffic = None
-    # per-rank share of the algorithmic bytes (rows are nnz-balanced across ranks)
+    # per-rank share of the algorithmic bytes (rows are cost-balanced across ranks)
     ach = (b_item + b_user) / world / ((t_item + t_user) * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "step": "one ALS sweep = item half-step + user half-step "
-                   "(+ factor all-gathers when sharded)", "launch": "one CUDA graph per half-step" if graphs_on else "plain launches", "rows": "nnz-balanced contiguous row shards per rank",
+                   "(+ factor all-gathers when sharded)", "launch": "one CUDA graph per half-step" if graphs_on else "plain launches", "rows": "cost-balanced (chunks + solve per row) contiguous row shards per rank",
                    "l2": "per-step inputs (2 CSR orientations + factors) exceed the 126 MB L2; no flush between steps",
                    "train_rmse_after_run": rmse_train},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(w["nnz"] * 12 // world),
