@@ -36,11 +36,11 @@ constexpr int kRowBytes = 128;               // one 64-wide bf16 MN atom row
 constexpr int kBlk = KC * kRowBytes;         // 4096: one [KC][64] block
 constexpr int kStageBytes = 3 * kBlk;        // H | L | R
 #ifndef HALS_WS_STAGES
-#define HALS_WS_STAGES 6
+#define HALS_WS_STAGES 10
 #endif
 constexpr int kStages = HALS_WS_STAGES;
 constexpr int kAcc = 4, kAccCols = 128;      // TMEM accumulators (N = 80 columns used of each 128)
-constexpr int kSlots = 3;
+constexpr int kSlots = 2;
 constexpr int kLd = 68;                      // hand-over row stride in floats: conflict-free 16-byte row stores
 constexpr int kSlotBytes = 2 * 64 * kLd * 4 + 512;   // S1 (h h^T rows) | S2 (l h^T rows) | b1 | b2
 constexpr int kSolvers = 9;
