@@ -89,3 +89,18 @@ def test_spark_als_model_directory_is_readable(tmp_path):
     (root / "metadata" / "part-00000").write_text(json.dumps({"rank": rank + 1}) + "\n")
     with pytest.raises(ValueError):
         read_spark_als_dir(str(root))
+
+
+def test_split_factor_layout_is_padded_by_owner_rank():
+    """SplitFactors (als_engine.py): rank q's rows [bounds[q], bounds[q+1]) live at [q * mx, q * mx + n_q) of the split
+    matrix, so that the all-gather of freshly solved rows is one in-place equal-size collective; the last row is the
+    all-zero row the ragged tail of a chunk gathers."""
+    from hybrid_als_twotower_recommender_b200.als_engine import SplitFactors
+    sf = SplitFactors([0, 3, 7, 7, 12], 4, "cpu", k=64)
+    assert sf.mx == 5 and sf.n_rows == 20 and tuple(sf.hl.shape) == (21, 128) and sf.hl.dtype == torch.bfloat16
+    assert sf.pad_of_h.tolist() == [0, 1, 2, 5, 6, 7, 8, 15, 16, 17, 18, 19]
+    assert all(tuple(sf.segment(q).shape) == (5, 128) for q in range(4))
+    assert sf.segment(2).data_ptr() == sf.hl[10:15].data_ptr()          # views into the one buffer (in-place all-gather)
+    assert float(sf.hl.abs().sum()) == 0.0
+    one = SplitFactors([0, 9], 1, "cpu", k=128)
+    assert one.mx == 9 and one.n_rows == 9 and tuple(one.hl.shape) == (10, 256) and one.pad_of_h.tolist() == list(range(9))
